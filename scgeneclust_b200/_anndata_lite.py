@@ -1,0 +1,125 @@
+"""Minimal AnnData stand-in.
+
+`anndata` is not installable in the build container (no network, no wheel), and the hot path only
+touches a small slice of the AnnData surface (`/root/reference/scGeneClust/_model.py:123-143`,
+`tl/information.py:53-54`, `tl/confidence.py:75-76`).  `AnnDataLite` implements exactly that slice with the
+same attribute names and mutation semantics so the stage functions in this package are written against the
+real contract.  When the real `anndata` package is importable it is accepted everywhere `AnnDataLite` is
+(see `is_anndata`).
+"""
+from __future__ import annotations
+
+import copy as _copy
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+from scipy.sparse import issparse
+
+try:  # pragma: no cover - not available in the build container
+    import anndata as _ad
+
+    _REAL_ANNDATA = (_ad.AnnData,)
+except Exception:  # noqa: BLE001
+    _REAL_ANNDATA = ()
+
+
+class AnnDataLite:
+    """`n_obs` x `n_vars` annotated matrix: `.X`, `.obs`, `.var`, `.obsm`, `.varm`, `.obsp`, `.varp`, `.uns`."""
+
+    def __init__(self, X, obs: Optional[pd.DataFrame] = None, var: Optional[pd.DataFrame] = None,
+                 obs_names=None, var_names=None):
+        if not (issparse(X) or isinstance(X, np.ndarray)):
+            X = np.asarray(X)
+        if X.ndim != 2:
+            raise ValueError(f"X must be 2-D, got shape {X.shape}")
+        self._X = X
+        n_obs, n_vars = X.shape
+        if obs is None:
+            names = obs_names if obs_names is not None else [f"cell_{i}" for i in range(n_obs)]
+            obs = pd.DataFrame(index=pd.Index(np.asarray(names, dtype=object)))
+        if var is None:
+            names = var_names if var_names is not None else [f"gene_{i}" for i in range(n_vars)]
+            var = pd.DataFrame(index=pd.Index(np.asarray(names, dtype=object)))
+        if len(obs) != n_obs or len(var) != n_vars:
+            raise ValueError("obs/var length does not match X")
+        self.obs, self.var = obs, var
+        self.obsm, self.varm, self.obsp, self.varp, self.uns = {}, {}, {}, {}, {}
+        self.raw = None
+
+    # -- shape / names --------------------------------------------------------------------------------------
+    @property
+    def X(self):
+        return self._X
+
+    @X.setter
+    def X(self, value):
+        if value.shape != self._X.shape:
+            raise ValueError(f"X has shape {self._X.shape}, cannot assign shape {value.shape}")
+        self._X = value
+
+    @property
+    def n_obs(self) -> int:
+        return self._X.shape[0]
+
+    @property
+    def n_vars(self) -> int:
+        return self._X.shape[1]
+
+    @property
+    def shape(self):
+        return self._X.shape
+
+    @property
+    def obs_names(self) -> pd.Index:
+        return self.obs.index
+
+    @property
+    def var_names(self) -> pd.Index:
+        return self.var.index
+
+    # -- copy / subset --------------------------------------------------------------------------------------
+    def copy(self) -> "AnnDataLite":
+        new = AnnDataLite(self._X.copy(), self.obs.copy(), self.var.copy())
+        for slot in ("obsm", "varm", "obsp", "varp"):
+            setattr(new, slot, {k: np.array(v, copy=True) for k, v in getattr(self, slot).items()})
+        new.uns = _copy.deepcopy(self.uns)
+        return new
+
+    def _resolve(self, index, names: pd.Index) -> np.ndarray:
+        index = np.asarray(index)
+        if index.dtype == bool:
+            if index.shape[0] != len(names):
+                raise IndexError("boolean index has wrong length")
+            return np.flatnonzero(index)
+        if index.dtype.kind in "iu":
+            return index.astype(np.intp)
+        pos = names.get_indexer(index)
+        if (pos < 0).any():
+            raise KeyError(f"names not found: {list(index[pos < 0][:5])}")
+        return pos
+
+    def _inplace_subset_var(self, index) -> None:
+        pos = self._resolve(index, self.var.index)
+        self._X = self._X[:, pos]
+        self.var = self.var.iloc[pos].copy()
+        self.varm = {k: np.asarray(v)[pos] for k, v in self.varm.items()}
+        self.varp = {k: np.asarray(v)[np.ix_(pos, pos)] for k, v in self.varp.items()}
+
+    def _inplace_subset_obs(self, index) -> None:
+        pos = self._resolve(index, self.obs.index)
+        self._X = self._X[pos, :]
+        self.obs = self.obs.iloc[pos].copy()
+        self.obsm = {k: np.asarray(v)[pos] for k, v in self.obsm.items()}
+        self.obsp = {k: np.asarray(v)[np.ix_(pos, pos)] for k, v in self.obsp.items()}
+
+    def __repr__(self) -> str:
+        return (f"AnnDataLite object with n_obs x n_vars = {self.n_obs} x {self.n_vars}\n"
+                f"    obs: {list(self.obs.columns)}\n    var: {list(self.var.columns)}\n"
+                f"    uns: {list(self.uns)}\n    obsm: {list(self.obsm)}\n    varm: {list(self.varm)}\n"
+                f"    varp: {list(self.varp)}")
+
+
+def is_anndata(obj) -> bool:
+    """True for `AnnDataLite` and, when importable, for real `anndata.AnnData`."""
+    return isinstance(obj, (AnnDataLite,) + _REAL_ANNDATA)
