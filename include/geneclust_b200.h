@@ -1,0 +1,188 @@
+/* geneclust_b200.h - C ABI of libgeneclust_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the gene-grouping hot path of GeneClust (ToryDeng/scGeneClust).  The reference has no
+ * FFI layer: its boundary is the Python stage functions that mutate an AnnData.  Each
+ * entry point below replaces the third-party native arithmetic one of those stage functions runs today; the
+ * reference line it replaces is cited on every declaration (paths relative to the reference checkout).  The
+ * Python binding a maintainer would add is shown in INTEGRATION.md; this repo's own host side
+ * (scgeneclust_b200/_lib.py) binds exactly these symbols with ctypes.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer (caller-owned, e.g. torch tensor storage) unless its name ends in
+ *     `_host`.  Outputs are preallocated by the caller.  No ownership is transferred.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued on it; calls do not synchronise unless
+ *     stated.  Calls are re-entrant per (device, stream).
+ *   - Return value: 0 on success, non-zero on error; gc_last_error() returns a thread-local message.
+ *   - Matrices are row-major.  "counts" is the cells x genes raw-count matrix stored as uint16.
+ */
+#ifndef GENECLUST_B200_H
+#define GENECLUST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GC_ABI_VERSION 1
+
+int gc_abi_version(void);
+const char *gc_last_error(void);
+/* Number of kernels this library has launched in the calling process (all streams); bench.py's gpu_launches. */
+long long gc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Ingest.  Replaces the host densification at scGeneClust/_model.py:123-124 and the integer check at
+ * scGeneClust/_validation.py:68-70.
+ * ------------------------------------------------------------------------------------------------------- */
+/* CSR (float32 data, int32 indices, int64 indptr, `n_rows` rows starting at global row `row0` of the dense
+ * matrix) -> dense uint16 counts[C x ld].  flags[0] is set to 1 if a value is not a non-negative integer,
+ * flags[1] to 1 if a value exceeds 65535.  The destination rows must be zeroed by the caller. */
+int gc_csr_to_counts(const float *data, const int32_t *indices, const int64_t *indptr, int64_t n_rows,
+                     int64_t row0, uint16_t *counts, int64_t ld, int32_t *flags, void *stream);
+/* Dense float32 block (n_rows x G, leading dimension ld_src) -> uint16 counts rows [row0, row0+n_rows). */
+int gc_dense_to_counts(const float *src, int64_t ld_src, int64_t n_rows, int64_t G, int64_t row0,
+                       uint16_t *counts, int64_t ld, int32_t *flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a1  Analytic Pearson residuals.  Replaces scanpy normalize_pearson_residuals called at
+ * scGeneClust/pp/_preprocessing.py:29.  The residual matrix is never required to be materialised: the
+ * statistics below fully determine Z[c,g] = clip((x - mu)/sqrt(mu + mu^2/theta), +-sqrt(C)), mu = r_c*s_g/T.
+ * ------------------------------------------------------------------------------------------------------- */
+/* Exact integer row sums (per cell, C), column sums (per gene, G) of counts[C x G]; outputs are uint64 and
+ * are ACCUMULATED into (zero them first), so a gene-sharded caller can all-reduce row sums. */
+int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, unsigned long long *row_sum,
+                  unsigned long long *col_sum, void *stream);
+/* Materialise Z (float32, C x G, leading dimension ldz) - used by the ps path, which needs adata.X = residuals
+ * (scGeneClust/tl/information.py:46,119), and by tests. */
+int gc_pearson_residuals(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, const float *row_sum_f,
+                         const float *col_sum_f, float total, float theta, float clip, float *Z, int64_t ldz,
+                         void *stream);
+/* Per-cell and per-gene SUMS of Z in float64 (accumulated into the outputs; zero them first).  The PCA
+ * centring vectors of sklearn PCA (decomposition/_pca.py:733-735) are these sums divided by G resp. C. */
+int gc_residual_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, const float *row_sum_f,
+                     const float *col_sum_f, float total, float theta, float clip, double *zrow_sum,
+                     double *zcol_sum, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a2  Gene-by-cell embedding.  Replaces the BLAS passes of sklearn randomized SVD
+ * (utils/extmath.py:377-383, :606) reached from sc.pp.pca at scGeneClust/pp/_preprocessing.py:52,54.
+ * M = Z - row_shift[c] - col_shift[g] is applied implicitly (fused residual producer, implicit centring).
+ *   trans = 0:  Y[C x q] = M  @ Qin[G x q]      (contract over genes)
+ *   trans = 1:  Y[G x q] = M^T @ Qin[C x q]     (contract over cells)
+ * q <= 64; Qin/Y have leading dimension 64 (columns q..63 are ignored / written as zero).
+ * `partials` is scratch of gc_rsvd_scratch_bytes(); results are deterministic (fixed reduction order).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint16_t *counts; int64_t C, G, ld;
+    const float *row_sum_f, *col_sum_f; float total, theta, clip;
+    const float *row_shift;   /* C or NULL */
+    const float *col_shift;   /* G or NULL */
+} gc_residual_matrix;
+
+int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G);
+int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *partials,
+                  void *stream);
+/* The SIMT (FFMA, exact float32 products) implementation of the same pass; kept as the on-device cross-check of
+ * the tensor-core kernel. */
+int gc_rsvd_apply_simt(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *partials,
+                       void *stream);
+/* Small panel algebra on tall-skinny panels (rows x 64, float32):
+ *   gram:  Gm[64 x 64] (float64) = P^T P   (deterministic two-stage reduction; scratch >= gc_gram_scratch_bytes)
+ *   right-multiply: Pout = P @ R[64 x 64] (R float32, row-major) */
+int64_t gc_gram_scratch_bytes(int64_t rows);
+int gc_panel_gram(const float *P, int64_t rows, double *Gm, void *scratch, void *stream);
+int gc_panel_matmul(const float *P, int64_t rows, const float *R, float *Pout, void *stream);
+/* Column-wise index of the max-|.| entry of P[rows x 64] @ R (for svd_flip, utils/extmath.py:975-981):
+ * out_val[j] = the signed entry of largest magnitude in column j (first index on ties). */
+int gc_panel_colabsmax(const float *P, int64_t rows, const float *R, float *out_val, void *scratch, void *stream);
+/* q x q float64 algebra on one CTA (replaces LAPACK getrf/geqrf/gesdd of utils/extmath.py:377-386, :606-619):
+ *   gc_chol_inv: Gm = L L^T (leading q x q of a 64 x 64 row-major matrix); Rinv = (L^-1)^T as float32 64 x 64, so
+ *                P @ Rinv is orthonormal when Gm = P^T P.  status[0] |= 1 on a non-positive pivot.
+ *   gc_sym_eig:  eigenvalues (descending, evals[64]) and eigenvectors (columns of U32 / optional U64) by cyclic Jacobi.
+ *   gc_scale_cols: R[:, j] *= sign(sign_src[j]) * scale[j] (either may be NULL) for j < q, zero for j >= q. */
+int gc_chol_inv(const double *Gm, int q, float *Rinv, int32_t *status, void *stream);
+int gc_sym_eig(const double *Gm, int q, double *evals, float *U32, double *U64, void *stream);
+int gc_scale_cols(float *R, const float *sign_src, const double *scale, int q, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a3/a4  GeneClust-fast gene k-means.  Replaces sklearn's Cython/OpenMP/sgemm kernels reached from
+ * MiniBatchKMeans.fit_predict at scGeneClust/tl/cluster.py:66-70 and paired_distances at :101.
+ * X is n x d float32 (d <= 64), centers K x d float32.
+ * ------------------------------------------------------------------------------------------------------- */
+/* labels[s] = argmin_j (|c_j|^2 - 2 x.c_j) with first-index ties (cluster/_k_means_lloyd.pyx:201-211);
+ * sqdist[s] = |x - c_label|^2 summed in the 4-way order of _euclidean_dense_dense (_k_means_common.pyx:16-43).
+ * If `gather` != NULL sample s is row gather[s] of X. */
+int gc_kmeans_assign(const float *X, int64_t ldx, const int32_t *gather, int64_t n, const float *centers,
+                     int K, int d, int32_t *labels, float *sqdist, void *stream);
+/* One dense minibatch centre update with unit sample weights (cluster/_k_means_minibatch.pyx:60-108):
+ * sequential float32 accumulation in sample order, weight_sums updated in place. */
+int gc_kmeans_minibatch_update(const float *X, int64_t ldx, const int32_t *gather, int64_t n,
+                               const int32_t *labels, const float *centers_old, float *centers_new,
+                               float *weight_sums, int K, int d, void *stream);
+/* Squared euclidean distances of every row of X to `ncand` candidate rows, computed in float64 and rounded
+ * to float32, clamped at 0 (metrics/pairwise.py _euclidean_distances float32 upcast path) - the k-means++
+ * building block (cluster/_kmeans.py:231-262).  out is ncand x n. */
+int gc_sqdist_to_rows(const float *X, int64_t ldx, int64_t n, int d, const int32_t *cand, int ncand,
+                      float *out, void *stream);
+/* k-means++ seeding (cluster/_kmeans.py:180-275), device resident: the K-1 greedy rounds are enqueued back to back.
+ * The host supplies the first centre id (its RandomState.choice draw) and the (K-1) x n_trials uniforms it drew
+ * (their number does not depend on the data).  Potentials are float64 sums rounded to float32; the cumulative sum
+ * searched by np.searchsorted is the sequential float32 np.cumsum.  ws: gc_kmeanspp_scratch_bytes(n, n_trials). */
+int64_t gc_kmeanspp_scratch_bytes(int64_t n, int n_trials);
+int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, int K, int32_t first_center,
+                     const double *uniforms, int n_trials, void *ws, float *centers_out, int32_t *indices_out,
+                     void *stream);
+/* out[0] = float64 sum of a float32 vector in a fixed order (batch inertia, cluster/_k_means_common.pyx:94-124). */
+int gc_sum_f32(const float *v, int64_t n, double *out, void *stream);
+/* dist[s] = |x_s - centers[labels[s]]|_2 (paired_distances, scGeneClust/tl/cluster.py:101). */
+int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, const float *centers, const int32_t *labels,
+                   float *dist, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a6/a7/a8  kNN mutual information (GeneClust-ps).  Replaces sklearn mutual_info_classif /
+ * mutual_info_regression (feature_selection/_mutual_info.py:20-153, :294-315) called per gene / per pair /
+ * per MST edge at scGeneClust/tl/information.py:24, :63, :96.  k = 3 neighbours.
+ * ------------------------------------------------------------------------------------------------------- */
+/* Input preparation of `_estimate_mi` (scale + 1e-10 noise), bit-exact incl. numpy's pairwise summation.
+ * Z: float32, row-major, `ldz`; column g of Z restricted to rows order[seg_off[c] .. seg_off[c+1]) is one
+ * slice.  For every (gene g < G, segment c < n_seg):
+ *   XR[g*n_tot + r] = feature-role (float64 path) value, YR[...] = target-role (float32 path) value,
+ * r running over seg_off[c]..seg_off[c+1].  xi1/xi2: noise vectors laid out like the segments (n_tot).
+ * YR/xi2 may be NULL. */
+int gc_mi_prepare(const float *Z, int64_t ldz, const int32_t *order, const int32_t *seg_off, int n_seg,
+                  int64_t G, int64_t n_tot, const double *xi1, const double *xi2, double *XR, double *YR,
+                  void *stream);
+/* KSG MI for gene pairs in itertools.combinations order, condensed index p in [p_begin, p_end):
+ * pair (i<j) uses XR[i, :n] and YR[j, :n] (n <= 64).  psi[m] = digamma(m), m = 0..n (psi[0] unused).
+ * mi_condensed[p - p_begin] always written; if dense != NULL also dense[i*N+j] = dense[j*N+i] = mi.
+ * nx_out/ny_out (uint8, (p_end-p_begin) x n) optional: the integer neighbour counts. */
+int gc_mi_cc_pairs(const double *XR, const double *YR, int64_t N, int n, int64_t ldr, const double *psi,
+                   int64_t p_begin, int64_t p_end, double *mi_condensed, double *dense, uint8_t *nx_out,
+                   uint8_t *ny_out, void *stream);
+/* KSG MI for arbitrary-length problems (complementarity: one problem per (MST edge, cell cluster)):
+ * problem q uses x = XR + x_off[q], y = YR + y_off[q], length len[q].  nx/ny scratch: int32, sum(len).
+ * out_off[q] = offset of problem q in nx/ny.  mi[q] written. */
+int gc_mi_cc_problems(const double *XR, const double *YR, const int64_t *x_off, const int64_t *y_off,
+                      const int32_t *len, const int64_t *out_off, int64_t n_prob, const double *psi,
+                      int32_t *nx, int32_t *ny, double *mi, void *stream);
+/* Ross MI of G prepared feature vectors (XR[g*ldr + s], s < n) against integer labels.
+ * label[s] in [0, n_label); label_k[l] = min(3, count_l - 1) (0 => samples of that label are ignored, they
+ * are the "unique label" points).  const_term = digamma(n_kept) + mean digamma(k) - mean digamma(count)
+ * (host, gene independent).  m_all: int32 scratch, n x G ([s*G+g]); mi[g] written. */
+int gc_mi_cd(const double *XR, int64_t ldr, int64_t G, int n, const int32_t *label, const int32_t *label_k,
+             int n_label, double const_term, const double *psi, int32_t *m_all, double *mi, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Synthetic negative-binomial counts (bench/test harness): counter-based, bit-identical
+ * to oracle/synth.py.  Writes rows [c0, c0+nc) x genes [g0, g0+ng) of the global matrix into counts[nc x ld].
+ * ------------------------------------------------------------------------------------------------------- */
+int gc_synth_counts(uint64_t seed, int64_t c0, int64_t nc, int64_t g0, int64_t ng, const double *gene_mean,
+                    const double *type_fc /* G_total x n_types */, int n_types, const int32_t *gene_module,
+                    const double *size_levels, int n_size, const double *module_levels, int n_modlev,
+                    int n_modules, uint16_t *counts, int64_t ld, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENECLUST_B200_H */

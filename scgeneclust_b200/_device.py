@@ -1,0 +1,335 @@
+"""Device-resident data for the hot path: the uint16 count matrix, the implicit Pearson-residual operator and the
+randomized-SVD driver that runs on it.  torch is used for allocation, streams and tiny elementwise glue only; every
+pass over the data is a kernel of libgeneclust_b200.so called through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+from scipy.sparse import issparse
+
+from ._lib import ResidualMatrix, lib, ptr, require_cuda, stream_handle
+
+THETA = 100.0  # scanpy normalize_pearson_residuals default (call site: scGeneClust/pp/_preprocessing.py:29)
+N_PCS = 50     # scanpy.settings.N_PCS, the n_comps default of sc.pp.pca (pp/_preprocessing.py:52)
+N_OVERSAMPLES = 10
+Q_LD = 64      # panel leading dimension used by the kernels
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# -------------------------------------------------------------------------------------------------------------
+# ingest
+# -------------------------------------------------------------------------------------------------------------
+@dataclass
+class DeviceCounts:
+    """cells x genes raw counts on the device, uint16, row-major with leading dimension `ld` (multiple of 64,
+    padding columns are zero).  Stored in an int16 tensor (bit pattern is what matters)."""
+    data: torch.Tensor
+    C: int
+    G: int
+
+    @property
+    def ld(self) -> int:
+        return self.data.shape[1]
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def to_numpy(self) -> np.ndarray:
+        return self.data[:, :self.G].cpu().numpy().view(np.uint16)
+
+
+def _check_flags(flags: torch.Tensor):
+    f = flags.cpu().numpy()
+    if f[0]:
+        # same message as the reference, scGeneClust/_validation.py:70
+        raise ValueError("Expected raw counts, got normalized counts possibly.")
+    if f[1]:
+        raise ValueError("Counts above 65535 are not supported by the uint16 device layout.")
+
+
+def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
+    """Host (or device) count matrix -> `DeviceCounts`.  Never densifies on the host (contrast
+    scGeneClust/_model.py:124, _validation.py:68): CSR is expanded and validated on the device."""
+    require_cuda()
+    L = lib()
+    dev = torch.device(device)
+    if isinstance(X, DeviceCounts):
+        return X
+    if isinstance(X, torch.Tensor):
+        if X.dtype not in (torch.int16, torch.uint16):
+            raise TypeError("device tensors must already be uint16/int16 counts")
+        C_, G_ = X.shape
+        ld = _round_up(G_, 64)
+        if X.device.type == "cuda" and G_ == ld and X.is_contiguous():
+            return DeviceCounts(X.view(torch.int16), C_, G_)
+        out = torch.zeros((C_, ld), dtype=torch.int16, device=dev)
+        out[:, :G_] = X.view(torch.int16).to(dev)
+        return DeviceCounts(out, C_, G_)
+    C_, G_ = X.shape
+    ld = _round_up(G_, 64)
+    counts = torch.zeros((C_, ld), dtype=torch.int16, device=dev)
+    flags = torch.zeros(2, dtype=torch.int32, device=dev)
+    st = stream_handle()
+    if issparse(X):
+        X = X.tocsr()
+        indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        data = X.data if X.data.dtype == np.float32 else X.data.astype(np.float32)
+        indices = X.indices if X.indices.dtype == np.int32 else X.indices.astype(np.int32)
+        d_indptr = torch.from_numpy(indptr).to(dev, non_blocking=True)
+        # one bulk copy of values and indices (pinned when the caller provides pinned memory)
+        d_data = torch.from_numpy(np.ascontiguousarray(data)).to(dev, non_blocking=True)
+        d_idx = torch.from_numpy(np.ascontiguousarray(indices)).to(dev, non_blocking=True)
+        L.csr_to_counts(ptr(d_data), ptr(d_idx), ptr(d_indptr), C_, 0, ptr(counts), ld, ptr(flags), st)
+    else:
+        Xh = np.asarray(X)
+        if Xh.dtype == np.uint16 or Xh.dtype == np.int16:
+            counts[:, :G_] = torch.from_numpy(np.ascontiguousarray(Xh).view(np.int16)).to(dev)
+        else:
+            for r0 in range(0, C_, rows_per_chunk):
+                blk = np.ascontiguousarray(Xh[r0:r0 + rows_per_chunk], dtype=np.float32)
+                d_blk = torch.from_numpy(blk).to(dev, non_blocking=True)
+                L.dense_to_counts(ptr(d_blk), G_, blk.shape[0], G_, r0, ptr(counts), ld, ptr(flags), st)
+    _check_flags(flags)
+    return DeviceCounts(counts, C_, G_)
+
+
+# -------------------------------------------------------------------------------------------------------------
+# implicit Pearson-residual matrix
+# -------------------------------------------------------------------------------------------------------------
+@dataclass
+class ResidualOperator:
+    """Z[c,g] = clip((x - mu)/sqrt(mu + mu^2/theta), +-sqrt(C)), mu = r_c s_g / T, as an operator on the device
+    counts; optional PCA centring shifts are applied implicitly by the pass kernels."""
+    counts: DeviceCounts
+    row_sum: torch.Tensor      # int64 [C]   exact
+    col_sum: torch.Tensor      # int64 [G]   exact
+    row_sum_f: torch.Tensor    # float32 [C]
+    col_sum_f: torch.Tensor    # float32 [G]
+    total: float
+    theta: float
+    clip: float
+    _scratch: Optional[torch.Tensor] = field(default=None, repr=False)
+
+    @property
+    def C(self) -> int:
+        return self.counts.C
+
+    @property
+    def G(self) -> int:
+        return self.counts.G
+
+    @classmethod
+    def from_counts(cls, counts: DeviceCounts, theta: float = THETA, comm=None) -> "ResidualOperator":
+        """`comm`: optional gene-shard communicator (scgeneclust_b200.dist.GeneShardComm); row sums and the
+        total are all-reduced over it so every shard uses the statistics of the full matrix."""
+        L = lib()
+        dev = counts.device
+        row_sum = torch.zeros(counts.C, dtype=torch.int64, device=dev)
+        col_sum = torch.zeros(counts.G, dtype=torch.int64, device=dev)
+        L.count_sums(ptr(counts.data), counts.C, counts.G, counts.ld, ptr(row_sum), ptr(col_sum), stream_handle())
+        n_cells = counts.C
+        if comm is not None:
+            comm.all_reduce_sum(row_sum)
+        total = float(row_sum.sum().item())
+        if total <= 0:
+            raise ValueError("count matrix is empty")
+        if bool((col_sum == 0).any().item()) or bool((row_sum == 0).any().item()):
+            # the reference yields NaN residuals here (0/0) and sklearn PCA then raises on NaN input
+            raise ValueError("Input contains all-zero genes or cells: Pearson residuals would be NaN. "
+                             "Filter them first (the reference's loader uses min_cells=3).")
+        return cls(counts, row_sum, col_sum, row_sum.to(torch.float32), col_sum.to(torch.float32),
+                   total, float(theta), float(np.float32(np.sqrt(n_cells))))
+
+    def struct(self, row_shift=None, col_shift=None) -> ResidualMatrix:
+        return ResidualMatrix(ptr(self.counts.data), self.C, self.G, self.counts.ld, ptr(self.row_sum_f),
+                              ptr(self.col_sum_f), self.total, self.theta, self.clip, ptr(row_shift), ptr(col_shift))
+
+    def _scratch_buf(self) -> torch.Tensor:
+        need = lib().rsvd_scratch_bytes(self.C, self.G)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.counts.device)
+        return self._scratch
+
+    def apply(self, trans: int, Q: torch.Tensor, row_shift=None, col_shift=None, out=None, simt: bool = False):
+        """trans=0: (C x 64) = M @ Q(G x 64);  trans=1: (G x 64) = M^T @ Q(C x 64)."""
+        n_in, n_out = (self.G, self.C) if trans == 0 else (self.C, self.G)
+        assert Q.shape == (n_in, Q_LD) and Q.dtype == torch.float32
+        if out is None:
+            out = torch.empty((n_out, Q_LD), dtype=torch.float32, device=Q.device)
+        m = self.struct(row_shift, col_shift)
+        fn = lib().rsvd_apply_simt if simt else lib().rsvd_apply
+        fn(C.byref(m), trans, ptr(Q), ptr(out), Q_LD, ptr(self._scratch_buf()), stream_handle())
+        return out
+
+    def materialize(self) -> torch.Tensor:
+        """Dense float32 residual matrix (C x G) on the device (ps path / return_info)."""
+        Z = torch.empty((self.C, self.G), dtype=torch.float32, device=self.counts.device)
+        lib().pearson_residuals(ptr(self.counts.data), self.C, self.G, self.counts.ld, ptr(self.row_sum_f),
+                                ptr(self.col_sum_f), self.total, self.theta, self.clip, ptr(Z), self.G,
+                                stream_handle())
+        return Z
+
+    def residual_sums(self, rows: bool = True, cols: bool = False):
+        dev = self.counts.device
+        zr = torch.zeros(self.C, dtype=torch.float64, device=dev) if rows else None
+        zc = torch.zeros(self.G, dtype=torch.float64, device=dev) if cols else None
+        lib().residual_sums(ptr(self.counts.data), self.C, self.G, self.counts.ld, ptr(self.row_sum_f),
+                            ptr(self.col_sum_f), self.total, self.theta, self.clip, ptr(zr), ptr(zc), stream_handle())
+        return zr, zc
+
+
+# -------------------------------------------------------------------------------------------------------------
+# randomized PCA on the operator (sklearn PCA(svd_solver='auto') -> 'randomized'; utils/extmath.py:313-386,560-626)
+# -------------------------------------------------------------------------------------------------------------
+class PanelAlgebra:
+    """64-column panel helpers (Gram, Cholesky-QR, thin eigendecomposition) - all on the device."""
+
+    def __init__(self, device, max_rows: int):
+        self.dev = device
+        self.scratch = torch.empty(lib().gram_scratch_bytes(max_rows), dtype=torch.uint8, device=device)
+        self.gram = torch.empty((Q_LD, Q_LD), dtype=torch.float64, device=device)
+        self.rinv = torch.empty((Q_LD, Q_LD), dtype=torch.float32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def chol_qr(self, P: torch.Tensor, q: int, out: torch.Tensor, comm=None) -> torch.Tensor:
+        """out = P @ R^-1 with P^T P = R^T R (one Cholesky-QR step).  With `comm` the rows of P are sharded and
+        the Gram matrix is all-reduced."""
+        L, st = lib(), stream_handle()
+        L.panel_gram(ptr(P), P.shape[0], ptr(self.gram), ptr(self.scratch), st)
+        if comm is not None:
+            comm.all_reduce_sum(self.gram)
+        L.chol_inv(ptr(self.gram), q, ptr(self.rinv), ptr(self.status), st)
+        L.panel_matmul(ptr(P), P.shape[0], ptr(self.rinv), ptr(out), st)
+        return out
+
+
+def pca_solver(n_samples: int, n_features: int, n_comps: int) -> str:
+    """sklearn PCA 'auto' policy (decomposition/_pca.py:524-536)."""
+    if n_features <= 1000 and n_samples >= 10 * n_features:
+        return "covariance_eigh"
+    if max(n_samples, n_features) <= 500:
+        return "full"
+    if 1 <= n_comps < 0.8 * min(n_samples, n_features):
+        return "randomized"
+    return "full"
+
+
+def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_comps: Optional[int] = None,
+                   comm=None, simt: bool = False, info: Optional[dict] = None) -> torch.Tensor:
+    """PCA scores (n_samples x n_comps, float32, device) of the residual matrix.
+
+    samples='genes' is `sc.pp.pca(norm_counts.T)` (scGeneClust/pp/_preprocessing.py:52): samples are genes,
+    features are cells, centring = per-cell mean over genes.  samples='cells' is `sc.pp.pca(norm_counts)` (:54).
+    Follows sklearn's randomized solver step for step (same Omega, n_iter rule, transpose rule, v-based sign
+    flip); the LU/QR panel normalisers are replaced by Cholesky-QR, which spans the same subspace.
+    With `comm` (gene-sharded operator) panels in cell space are all-reduced and panels in gene space stay local.
+    """
+    L, st = lib(), stream_handle()
+    dev = op.counts.device
+    G_total = op.G if comm is None else comm.total_genes
+    n_samples, n_features = (G_total, op.C) if samples == "genes" else (op.C, G_total)
+    min_dim = min(n_samples, n_features)
+    if n_comps is None:
+        n_comps = min_dim - 1 if N_PCS >= min_dim else N_PCS     # scanpy's n_comps rule
+    solver = pca_solver(n_samples, n_features, n_comps)
+    if solver != "randomized":
+        raise NotImplementedError(
+            f"sklearn PCA(svd_solver='auto') picks '{solver}' for shape ({n_samples}, {n_features}); only the "
+            "randomized solver (the one the GeneClust configurations hit) is implemented on the device")
+    q = n_comps + N_OVERSAMPLES
+    if q > Q_LD:
+        raise NotImplementedError("n_components + 10 must be <= 64")
+    n_iter = 7 if n_comps < 0.1 * min_dim else 4
+    transpose = n_samples < n_features
+
+    # centring vector = mean over samples of every feature (decomposition/_pca.py:733-735)
+    if samples == "genes":
+        zr, _ = op.residual_sums(rows=True, cols=False)
+        if comm is not None:
+            comm.all_reduce_sum(zr)
+        row_shift, col_shift = (zr / float(G_total)).to(torch.float32), None
+        a_is_stored = transpose            # A (after sklearn's transpose) has the stored cells x genes orientation
+    else:
+        _, zc = op.residual_sums(rows=False, cols=True)
+        row_shift, col_shift = None, (zc / float(op.C)).to(torch.float32)
+        a_is_stored = not transpose
+    fwd = 0 if a_is_stored else 1          # trans flag of  A @ Q
+    bwd = 1 - fwd
+    # A.shape[1] = length of the Omega rows; trans=0 contracts genes, trans=1 contracts cells
+    n_in_total = G_total if fwd == 0 else op.C
+
+    # Omega exactly as sklearn draws it (utils/extmath.py:323-334): normal((A.shape[1], q)) cast to float32
+    omega = np.random.RandomState(random_state).normal(size=(n_in_total, q)).astype(np.float32)
+    if comm is not None and fwd == 0:
+        omega = omega[comm.gene_lo:comm.gene_hi]
+    Qp = torch.zeros((omega.shape[0], Q_LD), dtype=torch.float32, device=dev)
+    Qp[:, :q] = torch.from_numpy(omega).to(dev)
+
+    alg = PanelAlgebra(dev, max(op.C, op.G))
+    buf_c = torch.empty((op.C, Q_LD), dtype=torch.float32, device=dev)
+    buf_g = torch.empty((op.G, Q_LD), dtype=torch.float32, device=dev)
+    tmp_c, tmp_g = torch.empty_like(buf_c), torch.empty_like(buf_g)
+
+    def apply(trans, Qin):
+        out = tmp_c if trans == 0 else tmp_g
+        op.apply(trans, Qin, row_shift, col_shift, out=out, simt=simt)
+        if comm is not None and trans == 0:
+            comm.all_reduce_sum(out)       # cell-space panel = sum over gene shards
+        return out
+
+    def normalise(trans, Y):
+        # rows of Y: cells (replicated across shards) for trans=0, local genes for trans=1
+        dst = buf_c if trans == 0 else buf_g
+        return alg.chol_qr(Y, q, dst, comm if (comm is not None and trans == 1) else None)
+
+    Qcur = Qp
+    for _ in range(n_iter):
+        Qcur = normalise(fwd, apply(fwd, Qcur))
+        Qcur = normalise(bwd, apply(bwd, Qcur))
+    # final range: orthonormal basis by two Cholesky-QR steps (qr_normalizer of extmath.py:386)
+    Y = apply(fwd, Qcur)
+    sh = comm if (comm is not None and fwd == 1) else None
+    Q1 = alg.chol_qr(Y, q, buf_c if fwd == 0 else buf_g, sh)
+    Qf = alg.chol_qr(Q1, q, Y, sh)                       # second pass writes into the tmp buffer
+    Qf = Qf.clone()
+    Bt = apply(bwd, Qf)                                  # B^T = A^T Q  (A.shape[1] x q)
+    # thin SVD of B through the q x q eigenproblem  B B^T = Uhat S^2 Uhat^T  (float64, on the device)
+    L.panel_gram(ptr(Bt), Bt.shape[0], ptr(alg.gram), ptr(alg.scratch), st)
+    if comm is not None and bwd == 1:
+        comm.all_reduce_sum(alg.gram)
+    evals = torch.empty(Q_LD, dtype=torch.float64, device=dev)
+    uhat = torch.empty((Q_LD, Q_LD), dtype=torch.float32, device=dev)
+    L.sym_eig(ptr(alg.gram), q, ptr(evals), ptr(uhat), None, st)
+    sing = torch.sqrt(torch.clamp(evals, min=0.0))
+    sign_src = torch.empty(Q_LD, dtype=torch.float32, device=dev)
+    if not transpose:
+        # U = Q Uhat, Vt = S^-1 Uhat^T B ; scores = U S ; sign from the rows of Vt = columns of B^T Uhat
+        L.panel_colabsmax(ptr(Bt), Bt.shape[0], ptr(uhat), ptr(sign_src), ptr(alg.scratch), st)
+        if comm is not None and bwd == 1:
+            sign_src = comm.absmax_merge(sign_src)
+        L.scale_cols(ptr(uhat), ptr(sign_src), ptr(sing), n_comps, st)
+        base = Qf
+    else:
+        # U = (S^-1 Uhat^T B)^T, Vt = (Q Uhat)^T ; scores = U S = B^T Uhat ; sign from the columns of Q Uhat
+        L.panel_colabsmax(ptr(Qf), Qf.shape[0], ptr(uhat), ptr(sign_src), ptr(alg.scratch), st)
+        if comm is not None and fwd == 1:
+            sign_src = comm.absmax_merge(sign_src)
+        L.scale_cols(ptr(uhat), ptr(sign_src), None, n_comps, st)
+        base = Bt
+    scores = torch.empty((base.shape[0], Q_LD), dtype=torch.float32, device=dev)
+    L.panel_matmul(ptr(base), base.shape[0], ptr(uhat), ptr(scores), st)
+    if int(alg.status.item()) != 0:
+        raise FloatingPointError("Cholesky-QR panel normalisation hit a non-positive pivot (rank-deficient panel)")
+    if info is not None:
+        info.update(n_iter=n_iter, transpose=bool(transpose), q=q, n_comps=n_comps,
+                    singular_values=sing[:n_comps].cpu().numpy(), passes=2 * n_iter + 2)
+    return scores[:, :n_comps].contiguous()

@@ -1,0 +1,393 @@
+// GeneClust-fast gene k-means kernels: replace scikit-learn's Cython/OpenMP/BLAS kernels reached from
+// MiniBatchKMeans.fit_predict (scGeneClust/tl/cluster.py:66-70) and paired_distances (:101).
+// Compiled with -fmad=false; where sklearn's order of float32 operations is known it is reproduced.
+#include "common.cuh"
+
+namespace gc {
+
+constexpr int kDMax = 64;        // feature dimension bound (GeneClust uses 50 PCs)
+constexpr int kAssignThreads = 64;
+
+// ---------------------------------------------------------------------------------------------------------
+// assignment: one thread per sample, centres staged in shared memory (K*d floats + K norms)
+// labels = argmin_j (|c_j|^2 - 2 x.c_j), strict '<' => first index on ties (_k_means_lloyd.pyx:196-211)
+// sqdist = sum (x-c)^2 in the 4-way unrolled order of _euclidean_dense_dense (_k_means_common.pyx:16-43)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAssignThreads)
+kmeans_assign_kernel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ gather, int64_t n,
+                     const float *__restrict__ centers, int K, int d, int32_t *__restrict__ labels,
+                     float *__restrict__ sqdist) {
+    extern __shared__ float smem[];
+    float *sc = smem;            // K * d
+    float *sn = smem + K * d;    // K
+    for (int i = threadIdx.x; i < K * d; i += blockDim.x) sc[i] = centers[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        float s = 0.f;
+        for (int f = 0; f < d; ++f) s = fmaf(sc[j * d + f], sc[j * d + f], s);
+        sn[j] = s;
+    }
+    __syncthreads();
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int64_t row = gather ? gather[s] : s;
+    const float *xp = X + row * ldx;
+    float x[kDMax];
+#pragma unroll
+    for (int f = 0; f < kDMax; ++f) x[f] = f < d ? xp[f] : 0.f;
+
+    float best = 0.f;
+    int lab = 0;
+    for (int j = 0; j < K; ++j) {
+        const float *c = sc + j * d;
+        float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll
+        for (int f = 0; f < kDMax; f += 2) {
+            if (f < d) dot0 = fmaf(x[f], c[f], dot0);
+            if (f + 1 < d) dot1 = fmaf(x[f + 1], c[f + 1], dot1);
+        }
+        const float pd = fmaf(-2.0f, dot0 + dot1, sn[j]);
+        if (j == 0 || pd < best) { best = pd; lab = j; }
+    }
+    labels[s] = lab;
+    if (sqdist != nullptr) {
+        const float *c = sc + lab * d;
+        float result = 0.f;
+        const int n4 = d / 4;
+#pragma unroll
+        for (int i = 0; i < kDMax / 4; ++i) {
+            if (i < n4) {
+                const float t0 = x[4 * i] - c[4 * i], t1 = x[4 * i + 1] - c[4 * i + 1];
+                const float t2 = x[4 * i + 2] - c[4 * i + 2], t3 = x[4 * i + 3] - c[4 * i + 3];
+                result = result + (((t0 * t0 + t1 * t1) + t2 * t2) + t3 * t3);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < kDMax; ++f) {
+            if (f >= 4 * n4 && f < d) { const float t = x[f] - c[f]; result = result + t * t; }
+        }
+        sqdist[s] = result;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// minibatch centre update: one CTA per cluster, thread f owns feature f, samples visited in batch order
+// (_k_means_minibatch.pyx:60-108 with unit sample weights)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDMax)
+kmeans_minibatch_update_kernel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ gather,
+                               int64_t n, const int32_t *__restrict__ labels,
+                               const float *__restrict__ centers_old, float *__restrict__ centers_new,
+                               float *__restrict__ weight_sums, int K, int d) {
+    const int k = blockIdx.x, f = threadIdx.x;
+    float wsum = 0.f;
+    const float w_old = weight_sums[k];
+    float acc = f < d ? centers_old[k * d + f] * w_old : 0.f;
+    for (int64_t s = 0; s < n; ++s) {
+        if (labels[s] == k) {              // warp-uniform
+            wsum += 1.0f;
+            const int64_t row = gather ? gather[s] : s;
+            if (f < d) acc = acc + X[row * ldx + f];
+        }
+    }
+    __syncthreads();  // every thread has read weight_sums[k] before it is overwritten
+    if (wsum > 0.f) {
+        const float w_new = w_old + wsum;
+        const float alpha = 1.0f / w_new;
+        if (f < d) centers_new[k * d + f] = acc * alpha;
+        if (f == 0) weight_sums[k] = w_new;
+    } else if (f < d) {
+        centers_new[k * d + f] = centers_old[k * d + f];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// squared distances to candidate rows in float64, rounded to float32, clamped at 0
+// (metrics/pairwise.py::_euclidean_distances_upcast: d = -2*x.y ; d += |x|^2 ; d += |y|^2 ; astype(float32))
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqdist_upcast(const float *__restrict__ xc, double xx, const float *__restrict__ y,
+                                               int d) {
+    double dot = 0.0, yy = 0.0;
+    for (int f = 0; f < d; ++f) {
+        const double yv = (double)y[f];
+        dot = fma((double)xc[f], yv, dot);
+        yy = fma(yv, yv, yy);
+    }
+    double v = -2.0 * dot;
+    v = v + xx;
+    v = v + yy;
+    const float r = (float)v;
+    return r > 0.f ? r : 0.f;
+}
+
+__global__ void sqdist_to_rows_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d,
+                                      const int32_t *__restrict__ cand, int ncand, float *__restrict__ out) {
+    __shared__ float sc[kDMax];
+    __shared__ double sxx;
+    const int c = blockIdx.y;
+    const float *xc = X + (int64_t)cand[c] * ldx;
+    if (threadIdx.x < d) sc[threadIdx.x] = xc[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double xx = 0.0;
+        for (int f = 0; f < d; ++f) xx = fma((double)sc[f], (double)sc[f], xx);
+        sxx = xx;
+    }
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[(int64_t)c * n + i] = sqdist_upcast(sc, sxx, X + i * ldx, d);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k-means++ (cluster/_kmeans.py:180-275), device resident: all K-1 greedy rounds are enqueued back to back,
+// the host only supplies the first centre id and the uniforms it drew from RandomState (their number does
+// not depend on the data).  State lives in `ws` (see gc_kmeanspp_scratch_bytes).
+// ---------------------------------------------------------------------------------------------------------
+struct KppState {
+    float current_pot;
+    int32_t best;      // index into cand[] of the winning trial of the previous round
+    int32_t pad[2];
+};
+
+// round step A (1 CTA): adopt the previous winner, sequential float32 cumsum of closest_dist_sq (np.cumsum),
+// searchsorted(rand_vals) -> candidate ids.
+__global__ void __launch_bounds__(1024)
+kpp_pick_kernel(KppState *st, float *__restrict__ closest, const float *__restrict__ trial_dist, int64_t n,
+                const double *__restrict__ uniforms, int n_trials, int32_t *__restrict__ cand,
+                float *__restrict__ cumsum, int32_t *__restrict__ indices_out, int round) {
+    // closest <- trial_dist[best] (np.minimum result of the winning candidate), round >= 2 only
+    if (round >= 2) {
+        const float *src = trial_dist + (int64_t)st->best * n;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) closest[i] = src[i];
+        if (threadIdx.x == 0) indices_out[round - 1] = cand[st->best];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float acc = 0.f;
+        for (int64_t i = 0; i < n; ++i) { acc = acc + closest[i]; cumsum[i] = acc; }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_trials) {
+        const double rv = uniforms[(int64_t)(round - 1) * n_trials + threadIdx.x] * (double)st->current_pot;
+        // np.searchsorted(cumsum, rv, side='left'): first index with cumsum[idx] >= rv
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((double)cumsum[mid] < rv) lo = mid + 1; else hi = mid;
+        }
+        if (lo > n - 1) lo = n - 1;  // np.clip(candidate_ids, None, n - 1)
+        cand[threadIdx.x] = (int32_t)lo;
+    }
+}
+
+// round step B: trial_dist[c][i] = min(closest[i], dist(X[cand[c]], X[i])); per-CTA partial potentials (fp64)
+constexpr int kKppThreads = 256;
+__global__ void __launch_bounds__(kKppThreads)
+kpp_trial_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d, const int32_t *__restrict__ cand,
+                 const float *__restrict__ closest, float *__restrict__ trial_dist, double *__restrict__ partial) {
+    __shared__ float sc[kDMax];
+    __shared__ double sxx;
+    __shared__ double red[kKppThreads];
+    const int c = blockIdx.y;
+    const float *xc = X + (int64_t)cand[c] * ldx;
+    if (threadIdx.x < d) sc[threadIdx.x] = xc[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double xx = 0.0;
+        for (int f = 0; f < d; ++f) xx = fma((double)sc[f], (double)sc[f], xx);
+        sxx = xx;
+    }
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (i < n) {
+        const float dd = fminf(closest[i], sqdist_upcast(sc, sxx, X + i * ldx, d));
+        trial_dist[(int64_t)c * n + i] = dd;
+        v = (double)dd;
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = kKppThreads / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(int64_t)c * gridDim.x + blockIdx.x] = red[0];
+}
+
+// round step C (1 warp): candidates_pot = sum of partials (fixed order), first argmin, new current_pot
+__global__ void kpp_choose_kernel(KppState *st, const double *__restrict__ partial, int n_blocks, int n_trials) {
+    if (threadIdx.x == 0) {
+        float best_pot = 0.f;
+        int best = 0;
+        for (int c = 0; c < n_trials; ++c) {
+            double s = 0.0;
+            for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)c * n_blocks + b];
+            const float pot = (float)s;
+            if (c == 0 || pot < best_pot) { best_pot = pot; best = c; }
+        }
+        st->current_pot = best_pot;
+        st->best = best;
+    }
+}
+
+// first centre: closest = dist(X[first]), current_pot = sum
+__global__ void kpp_first_kernel(KppState *st, const double *__restrict__ partial, int n_blocks,
+                                 int32_t *__restrict__ cand, int32_t first, int32_t *__restrict__ indices_out) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partial[b];
+        st->current_pot = (float)s;
+        st->best = 0;
+        cand[0] = first;
+        indices_out[0] = first;
+    }
+}
+
+__global__ void kpp_set_cand_kernel(int32_t *cand, int32_t first) { cand[0] = first; }
+
+__global__ void kpp_finish_kernel(const KppState *st, const int32_t *__restrict__ cand,
+                                  int32_t *__restrict__ indices_out, int K) {
+    if (threadIdx.x == 0) indices_out[K - 1] = cand[st->best];
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ idx,
+                                   int n_rows, int d, float *__restrict__ out) {
+    const int r = blockIdx.x;
+    if (r < n_rows && threadIdx.x < d) out[r * d + threadIdx.x] = X[(int64_t)idx[r] * ldx + threadIdx.x];
+}
+
+// paired euclidean distance to the assigned centre (row_norms(X - Y), float32)
+__global__ void paired_dist_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d,
+                                   const float *__restrict__ centers, const int32_t *__restrict__ labels,
+                                   float *__restrict__ dist) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float *x = X + s * ldx, *c = centers + (int64_t)labels[s] * d;
+    float acc = 0.f;
+    for (int f = 0; f < d; ++f) { const float t = x[f] - c[f]; acc = acc + t * t; }
+    dist[s] = sqrtf(acc);
+}
+
+// deterministic float64 sum of a float32 vector (single CTA, fixed tree), result as float64 and float32
+__global__ void __launch_bounds__(1024) sum_f32_kernel(const float *__restrict__ v, int64_t n, double *out) {
+    __shared__ double red[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) s += (double)v[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+}  // namespace gc
+
+using namespace gc;
+
+extern "C" int gc_kmeans_assign(const float *X, int64_t ldx, const int32_t *gather, int64_t n, const float *centers,
+                                int K, int d, int32_t *labels, float *sqdist, void *stream) {
+    GC_REQUIRE(X && centers && labels, "null pointer");
+    GC_REQUIRE(d >= 1 && d <= kDMax, "d must be in [1, 64]");
+    GC_REQUIRE(K >= 1 && n >= 1 && ldx >= d, "bad shape");
+    const size_t smem = (size_t)(K * d + K) * sizeof(float);
+    GC_REQUIRE(smem <= 200 * 1024, "K*d too large for the shared-memory centre cache");
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        GC_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kmeans_assign_kernel<<<(unsigned)ceil_div<int64_t>(n, kAssignThreads), kAssignThreads, smem, as_stream(stream)>>>(
+        X, ldx, gather, n, centers, K, d, labels, sqdist);
+    return check_launch("kmeans_assign_kernel");
+}
+
+extern "C" int gc_kmeans_minibatch_update(const float *X, int64_t ldx, const int32_t *gather, int64_t n,
+                                          const int32_t *labels, const float *centers_old, float *centers_new,
+                                          float *weight_sums, int K, int d, void *stream) {
+    GC_REQUIRE(X && labels && centers_old && centers_new && weight_sums, "null pointer");
+    GC_REQUIRE(d >= 1 && d <= kDMax && K >= 1 && n >= 1, "bad shape");
+    kmeans_minibatch_update_kernel<<<K, kDMax, 0, as_stream(stream)>>>(X, ldx, gather, n, labels, centers_old,
+                                                                      centers_new, weight_sums, K, d);
+    return check_launch("kmeans_minibatch_update_kernel");
+}
+
+extern "C" int gc_sqdist_to_rows(const float *X, int64_t ldx, int64_t n, int d, const int32_t *cand, int ncand,
+                                 float *out, void *stream) {
+    GC_REQUIRE(X && cand && out, "null pointer");
+    GC_REQUIRE(d >= 1 && d <= kDMax && n >= 1 && ncand >= 1, "bad shape");
+    dim3 grid((unsigned)ceil_div<int64_t>(n, 256), (unsigned)ncand);
+    sqdist_to_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(X, ldx, n, d, cand, ncand, out);
+    return check_launch("sqdist_to_rows_kernel");
+}
+
+extern "C" int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, const float *centers,
+                              const int32_t *labels, float *dist, void *stream) {
+    GC_REQUIRE(X && centers && labels && dist, "null pointer");
+    paired_dist_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(X, ldx, n, d, centers,
+                                                                                          labels, dist);
+    return check_launch("paired_dist_kernel");
+}
+
+extern "C" int gc_sum_f32(const float *v, int64_t n, double *out, void *stream) {
+    GC_REQUIRE(v && out && n >= 1, "bad arguments");
+    sum_f32_kernel<<<1, 1024, 0, as_stream(stream)>>>(v, n, out);
+    return check_launch("sum_f32_kernel");
+}
+
+extern "C" int64_t gc_kmeanspp_scratch_bytes(int64_t n, int n_trials) {
+    const int64_t n_blocks = ceil_div<int64_t>(n, kKppThreads);
+    // state | cand[n_trials] | closest[n] | cumsum[n] | trial_dist[n_trials*n] | partial[n_trials*n_blocks]
+    return 256 + 256 + (int64_t)sizeof(float) * (2 * n + (int64_t)n_trials * n) + 256 * 3 +
+           (int64_t)sizeof(double) * n_trials * n_blocks + 256;
+}
+
+extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, int K, int32_t first_center,
+                                const double *uniforms, int n_trials, void *ws, float *centers_out,
+                                int32_t *indices_out, void *stream) {
+    GC_REQUIRE(X && uniforms && ws && centers_out && indices_out, "null pointer");
+    GC_REQUIRE(d >= 1 && d <= kDMax && K >= 1 && n >= K, "bad shape");
+    GC_REQUIRE(n_trials >= 1 && n_trials <= 32, "n_local_trials must be in [1, 32]");
+    GC_REQUIRE(first_center >= 0 && first_center < n, "first centre out of range");
+    cudaStream_t st = as_stream(stream);
+    const int n_blocks = (int)ceil_div<int64_t>(n, kKppThreads);
+    auto align = [](char *p) { return (char *)(((uintptr_t)p + 255) & ~(uintptr_t)255); };
+    char *p = align((char *)ws);
+    KppState *state = (KppState *)p;            p = align(p + sizeof(KppState));
+    int32_t *cand = (int32_t *)p;               p = align(p + sizeof(int32_t) * 32);
+    float *closest = (float *)p;                p = align(p + sizeof(float) * n);
+    float *cumsum = (float *)p;                 p = align(p + sizeof(float) * n);
+    float *trial = (float *)p;                  p = align(p + sizeof(float) * n * n_trials);
+    double *partial = (double *)p;
+
+    // first centre: closest_dist_sq = dist(centre0, X) (no min), current_pot = its sum
+    kpp_set_cand_kernel<<<1, 1, 0, st>>>(cand, first_center);
+    if (int rc = check_launch("kpp_set_cand_kernel")) return rc;
+    {
+        dim3 grid((unsigned)n_blocks, 1);
+        // closest starts at +inf so that min(closest, d) = d
+        GC_CUDA(cudaMemsetAsync(closest, 0x7f, sizeof(float) * n, st));  // 0x7f7f7f7f = 3.39e38 > any distance
+        kpp_trial_kernel<<<grid, kKppThreads, 0, st>>>(X, ldx, n, d, cand, closest, trial, partial);
+        if (int rc = check_launch("kpp_trial_kernel")) return rc;
+        kpp_first_kernel<<<1, 32, 0, st>>>(state, partial, n_blocks, cand, first_center, indices_out);
+        if (int rc = check_launch("kpp_first_kernel")) return rc;
+        GC_CUDA(cudaMemcpyAsync(closest, trial, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int round = 1; round < K; ++round) {
+        kpp_pick_kernel<<<1, 1024, 0, st>>>(state, closest, trial, n, uniforms, n_trials, cand, cumsum,
+                                            indices_out, round);
+        if (int rc = check_launch("kpp_pick_kernel")) return rc;
+        dim3 grid((unsigned)n_blocks, (unsigned)n_trials);
+        kpp_trial_kernel<<<grid, kKppThreads, 0, st>>>(X, ldx, n, d, cand, closest, trial, partial);
+        if (int rc = check_launch("kpp_trial_kernel")) return rc;
+        kpp_choose_kernel<<<1, 32, 0, st>>>(state, partial, n_blocks, n_trials);
+        if (int rc = check_launch("kpp_choose_kernel")) return rc;
+    }
+    if (K > 1) {
+        kpp_finish_kernel<<<1, 32, 0, st>>>(state, cand, indices_out, K);
+        if (int rc = check_launch("kpp_finish_kernel")) return rc;
+    }
+    gather_rows_kernel<<<K, kDMax, 0, st>>>(X, ldx, indices_out, K, d, centers_out);
+    return check_launch("gather_rows_kernel");
+}

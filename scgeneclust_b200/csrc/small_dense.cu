@@ -1,0 +1,192 @@
+// q x q (q <= 64) float64 dense algebra on one CTA: the panel normaliser and the thin SVD of randomized SVD
+// (replaces LAPACK getrf/geqrf/gesdd reached from sklearn utils/extmath.py:377-386, :606-619 via
+// scGeneClust/pp/_preprocessing.py:52).  Kept on the device so the 16 passes run without host round trips.
+#include "common.cuh"
+
+namespace gc {
+
+constexpr int kN = 64;
+
+// Cholesky Gm = L L^T of the leading q x q block, then Rinv = (L^-1)^T as float32 (64 x 64, zero padded), so that
+// P @ Rinv has orthonormal columns when Gm = P^T P.  status[0] |= 1 on a non-positive pivot.
+__global__ void __launch_bounds__(kN)
+chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, int32_t *status) {
+    extern __shared__ double dyn_smem[];
+    double (*L)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem);
+    double (*Li)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem + kN * (kN + 1));
+    const int i = threadIdx.x;
+    for (int j = 0; j < kN; ++j) { L[i][j] = (i < q && j < q) ? Gm[i * kN + j] : 0.0; Li[i][j] = 0.0; }
+    __syncthreads();
+    for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        if (i >= j && i < q) {
+            s = L[i][j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+        }
+        __syncthreads();
+        if (i == j) {
+            if (!(s > 0.0)) { atomicOr(status, 1); s = 1.0; }
+            L[j][j] = sqrt(s);
+        }
+        __syncthreads();
+        if (i > j && i < q) L[i][j] = s / L[j][j];
+        __syncthreads();
+    }
+    // inverse of the lower-triangular L: thread i solves column i of L X = I by forward substitution
+    if (i < q) {
+        for (int r = i; r < q; ++r) {
+            double s = r == i ? 1.0 : 0.0;
+            for (int k = i; k < r; ++k) s -= L[r][k] * Li[k][i];
+            Li[r][i] = s / L[r][r];
+        }
+    }
+    __syncthreads();
+    // Rinv[a][b] = (L^-1)^T[a][b] = Li[b][a]
+    for (int j = 0; j < kN; ++j) Rinv[i * kN + j] = (i < q && j < q) ? (float)Li[j][i] : 0.f;
+}
+
+// Symmetric eigendecomposition of the leading q x q block of Gm by cyclic two-sided Jacobi with the round-robin
+// parallel ordering.  Outputs eigenvalues in descending order (evals[64], zero padded) and the matching
+// eigenvectors as columns of U (float32 and float64, 64 x 64 row-major, zero padded).
+__global__ void __launch_bounds__(256)
+sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals, float *__restrict__ U32,
+               double *__restrict__ U64) {
+    extern __shared__ double dyn_smem[];
+    double (*A)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem);
+    double (*V)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem + kN * (kN + 1));
+    __shared__ double cs[kN / 2][2];
+    __shared__ int pp[kN / 2], qq[kN / 2];
+    __shared__ double off2, diag2;
+    __shared__ int order[kN];
+    const int tid = threadIdx.x;
+    const int m = (q + 1) & ~1;          // even number of players (one dummy when q is odd)
+    const int n_pairs = m / 2;
+    for (int idx = tid; idx < kN * kN; idx += 256) {
+        const int r = idx / kN, c = idx % kN;
+        A[r][c] = (r < q && c < q) ? Gm[r * kN + c] : 0.0;
+        V[r][c] = r == c ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        if (tid == 0) {
+            double o = 0.0, d = 0.0;
+            for (int r = 0; r < q; ++r) {
+                d += A[r][r] * A[r][r];
+                for (int c = r + 1; c < q; ++c) o += A[r][c] * A[r][c];
+            }
+            off2 = o; diag2 = d;
+        }
+        __syncthreads();
+        if (off2 <= 1e-32 * diag2) break;
+        for (int round = 0; round < m - 1; ++round) {
+            if (tid < n_pairs) {
+                // round-robin tournament: player m-1 fixed, the others rotate
+                int a = tid == 0 ? m - 1 : (round + tid) % (m - 1);
+                int b = (round + m - 1 - tid) % (m - 1);
+                if (a > b) { const int t = a; a = b; b = t; }
+                double c = 1.0, s = 0.0;
+                if (b < q && A[a][b] != 0.0) {
+                    const double apq = A[a][b], tau = (A[b][b] - A[a][a]) / (2.0 * apq);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    s = t * c;
+                }
+                pp[tid] = a; qq[tid] = b; cs[tid][0] = c; cs[tid][1] = s;
+            }
+            __syncthreads();
+            // A <- A J  (columns), V <- V J
+            for (int task = tid; task < n_pairs * q; task += 256) {
+                const int pr = task / q, r = task % q;
+                const int a = pp[pr], b = qq[pr];
+                if (b >= q) continue;
+                const double c = cs[pr][0], s = cs[pr][1];
+                const double x = A[r][a], y = A[r][b];
+                A[r][a] = c * x - s * y; A[r][b] = s * x + c * y;
+                const double vx = V[r][a], vy = V[r][b];
+                V[r][a] = c * vx - s * vy; V[r][b] = s * vx + c * vy;
+            }
+            __syncthreads();
+            // A <- J^T A  (rows)
+            for (int task = tid; task < n_pairs * q; task += 256) {
+                const int pr = task / q, col = task % q;
+                const int a = pp[pr], b = qq[pr];
+                if (b >= q) continue;
+                const double c = cs[pr][0], s = cs[pr][1];
+                const double x = A[a][col], y = A[b][col];
+                A[a][col] = c * x - s * y; A[b][col] = s * x + c * y;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // descending order by selection (rank counting), ties by index
+    if (tid < kN) {
+        if (tid < q) {
+            int rank = 0;
+            const double v = A[tid][tid];
+            for (int j = 0; j < q; ++j) {
+                const double w = A[j][j];
+                rank += (w > v) || (w == v && j < tid);
+            }
+            order[rank] = tid;
+        }
+    }
+    __syncthreads();
+    if (tid < kN) evals[tid] = tid < q ? A[order[tid]][order[tid]] : 0.0;
+    for (int idx = tid; idx < kN * kN; idx += 256) {
+        const int r = idx / kN, c = idx % kN;
+        const double v = (r < q && c < q) ? V[r][order[c]] : 0.0;
+        U32[idx] = (float)v;
+        if (U64) U64[idx] = v;
+    }
+}
+
+// R[:, j] *= sign(val[j]) * scale[j] for the leading q columns (svd_flip + optional column scaling)
+__global__ void scale_cols_kernel(float *__restrict__ R, const float *__restrict__ sign_src,
+                                  const double *__restrict__ scale, int q) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kN * kN) return;
+    const int c = idx % kN;
+    if (c >= q) { R[idx] = 0.f; return; }
+    double f = 1.0;
+    if (sign_src) f = sign_src[c] < 0.f ? -1.0 : (sign_src[c] > 0.f ? 1.0 : 0.0);   // np.sign
+    if (scale) f *= scale[c];
+    R[idx] = (float)((double)R[idx] * f);
+}
+
+}  // namespace gc
+
+using namespace gc;
+
+extern "C" int gc_chol_inv(const double *Gm, int q, float *Rinv, int32_t *status, void *stream) {
+    GC_REQUIRE(Gm && Rinv && status, "null pointer");
+    GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
+    const int smem = 2 * kN * (kN + 1) * (int)sizeof(double);
+    static thread_local bool configured = false;
+    if (!configured) {
+        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    chol_inv_kernel<<<1, kN, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
+    return check_launch("chol_inv_kernel");
+}
+
+extern "C" int gc_sym_eig(const double *Gm, int q, double *evals, float *U32, double *U64, void *stream) {
+    GC_REQUIRE(Gm && evals && U32, "null pointer");
+    GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
+    const int smem = 2 * kN * (kN + 1) * (int)sizeof(double);
+    static thread_local bool configured = false;
+    if (!configured) {
+        GC_CUDA(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    sym_eig_kernel<<<1, 256, smem, as_stream(stream)>>>(Gm, q, evals, U32, U64);
+    return check_launch("sym_eig_kernel");
+}
+
+extern "C" int gc_scale_cols(float *R, const float *sign_src, const double *scale, int q, void *stream) {
+    GC_REQUIRE(R != nullptr, "null pointer");
+    GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
+    scale_cols_kernel<<<kN * kN / 256, 256, 0, as_stream(stream)>>>(R, sign_src, scale, q);
+    return check_launch("scale_cols_kernel");
+}

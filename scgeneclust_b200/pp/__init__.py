@@ -1,0 +1,1 @@
+from ._preprocessing import normalize, reduce_dim

@@ -1,0 +1,71 @@
+"""Preprocessing stages with the reference's names and semantics (scGeneClust/pp/_preprocessing.py:15-55), running
+on the device.  Both functions mutate `adata` like the reference; device-resident state lives in
+`adata.uns['geneclust_b200']` (a `HotPathState`)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Literal, Optional
+
+import numpy as np
+import torch
+from loguru import logger
+
+from .._device import DeviceCounts, ResidualOperator, ingest_counts, randomized_pca
+
+STATE_KEY = "geneclust_b200"
+
+
+@dataclass
+class HotPathState:
+    """Device-side companions of the AnnData slots the reference fills."""
+    op: Optional[ResidualOperator] = None        # implicit adata.X (Pearson residuals)
+    Z: Optional[torch.Tensor] = None             # materialised residuals (ps path), float32 C x G
+    varm_pca: Optional[torch.Tensor] = None      # device copy of varm['X_pca']
+    obsm_pca: Optional[torch.Tensor] = None
+    comm: object = None                          # optional GeneShardComm
+    info: dict = field(default_factory=dict)
+
+
+def get_state(adata) -> HotPathState:
+    st = adata.uns.get(STATE_KEY)
+    if st is None:
+        st = HotPathState()
+        adata.uns[STATE_KEY] = st
+    return st
+
+
+def normalize(adata, modality: Literal['sc', 'st'] = 'sc', materialize: bool = False):
+    """`adata.X` (raw counts) -> analytic Pearson residuals (reference: pp/_preprocessing.py:15-29).
+
+    The counts go to the device once (uint16); the residual matrix is an implicit operator there.  `adata.X` is
+    overwritten with the dense float32 residuals only when `materialize=True` (GeneClust-ps and
+    `return_info=True` need them on the host); GeneClust-fast never materialises them.
+    """
+    logger.info("Preprocessing data...")
+    if modality != 'sc':
+        raise NotImplementedError("modality='st' (normalize_total + log1p, SpaGCN) is outside the B200 hot path")
+    st = get_state(adata)
+    counts = adata.X if isinstance(adata.X, DeviceCounts) else ingest_counts(adata.X)
+    st.op = ResidualOperator.from_counts(counts, comm=st.comm)
+    adata.uns['pearson_residuals_normalization'] = {'theta': st.op.theta, 'clip': None, 'computed_on': 'adata.X'}
+    if materialize:
+        st.Z = st.op.materialize()
+        adata.X = st.Z.cpu().numpy()
+
+
+def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):
+    """Gene-level PCA into `adata.varm['X_pca']` and, for GeneClust-ps, cell-level PCA into `adata.obsm['X_pca']`
+    (reference: pp/_preprocessing.py:35-55; sc.pp.pca -> sklearn PCA(50, svd_solver='auto') -> randomized SVD)."""
+    st = get_state(adata)
+    if st.op is None:
+        raise RuntimeError("reduce_dim called before normalize")
+    info = {}
+    st.varm_pca = randomized_pca(st.op, 'genes', random_state, comm=st.comm, info=info)
+    st.info['gene_pca'] = info
+    if st.comm is not None:
+        st.varm_pca = st.comm.all_gather_rows(st.varm_pca)
+    adata.varm['X_pca'] = st.varm_pca.cpu().numpy()
+    if version == 'ps':
+        st.obsm_pca = randomized_pca(st.op, 'cells', random_state, comm=st.comm)
+        adata.obsm['X_pca'] = st.obsm_pca.cpu().numpy()
+    logger.info("Data preprocessing done.")
