@@ -31,6 +31,14 @@ const char *gc_last_error(void);
 /* Number of kernels this library has launched in the calling process (all streams); bench.py's gpu_launches. */
 long long gc_launch_count(void);
 
+/* Device-time measurement with CUDA events on the launching stream (bench.py's roofline block).  While enabled, the
+ * entry points that launch a dominant kernel bracket exactly that kernel with an event pair:
+ *   slot 0 = the randomized-SVD pass kernel (gc_rsvd_apply, gc_rsvd_apply_simt), slot 1 = the KSG pair kernel
+ *   (gc_mi_cc_pairs).  gc_profile_collect synchronises the recorded events, returns their summed duration and
+ * count (host pointers) and clears the slot. */
+int gc_profile_enable(int on);
+int gc_profile_collect(int slot, double *total_ms_host, long long *launches_host);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Ingest.  Replaces the host densification at scGeneClust/_model.py:123-124 and the integer check at
  * scGeneClust/_validation.py:68-70.
@@ -138,6 +146,10 @@ int gc_sum_f32(const float *v, int64_t n, double *out, void *stream);
 /* dist[s] = |x_s - centers[labels[s]]|_2 (paired_distances, scGeneClust/tl/cluster.py:101). */
 int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, const float *centers, const int32_t *labels,
                    float *dist, void *stream);
+/* closeness[s] = 1 - minmax_scale(dist within the cluster of s) in float32, sklearn's `x * scale + min` form with
+ * scale = 1 / range (range < 10 eps -> 1) (scGeneClust/tl/cluster.py:102-104).  scratch: 2*K int32. */
+int gc_closeness(const float *dist, const int32_t *labels, int64_t n, int K, int32_t *scratch, float *closeness,
+                 void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * a6/a7/a8  kNN mutual information (GeneClust-ps).  Replaces sklearn mutual_info_classif /

@@ -29,7 +29,7 @@ class AnnDataLite:
 
     def __init__(self, X, obs: Optional[pd.DataFrame] = None, var: Optional[pd.DataFrame] = None,
                  obs_names=None, var_names=None):
-        if not (issparse(X) or isinstance(X, np.ndarray)):
+        if not (issparse(X) or isinstance(X, np.ndarray) or getattr(X, "is_device_counts", False)):
             X = np.asarray(X)
         if X.ndim != 2:
             raise ValueError(f"X must be 2-D, got shape {X.shape}")

@@ -33,7 +33,19 @@ class DeviceCounts:
     padding columns are zero).  Stored in an int16 tensor (bit pattern is what matters)."""
     data: torch.Tensor
     C: int
-    G: int
+    G: int                       # genes held by THIS rank
+    comm: object = None          # GeneShardComm when `data` is the gene shard [comm.gene_lo, comm.gene_hi)
+
+    is_device_counts = True     # lets AnnDataLite carry the device-resident matrix as `.X`
+    ndim = 2
+
+    @property
+    def shape(self):
+        """Shape of the GLOBAL matrix (cells x all genes), which is what the AnnData describes."""
+        return (self.C, self.G if self.comm is None else self.comm.total_genes)
+
+    def copy(self) -> "DeviceCounts":
+        return DeviceCounts(self.data.clone(), self.C, self.G, self.comm)
 
     @property
     def ld(self) -> int:
@@ -45,6 +57,21 @@ class DeviceCounts:
 
     def to_numpy(self) -> np.ndarray:
         return self.data[:, :self.G].cpu().numpy().view(np.uint16)
+
+
+@dataclass
+class HostShard:
+    """Host-resident gene shard of a count matrix for the multi-GPU entry: `array` is cells x local genes
+    (uint16, ideally pinned), `comm` says which genes of the global matrix they are."""
+    array: np.ndarray
+    comm: object
+
+    is_device_counts = True
+    ndim = 2
+
+    @property
+    def shape(self):
+        return (self.array.shape[0], self.comm.total_genes)
 
 
 def _check_flags(flags: torch.Tensor):
@@ -64,6 +91,12 @@ def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
     dev = torch.device(device)
     if isinstance(X, DeviceCounts):
         return X
+    if isinstance(X, HostShard):
+        local = ingest_counts(X.array, device, rows_per_chunk)
+        if local.G != X.comm.local_genes:
+            raise ValueError(f"host shard has {local.G} genes, the communicator assigns {X.comm.local_genes}")
+        local.comm = X.comm
+        return local
     if isinstance(X, torch.Tensor):
         if X.dtype not in (torch.int16, torch.uint16):
             raise TypeError("device tensors must already be uint16/int16 counts")
@@ -92,7 +125,11 @@ def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
     else:
         Xh = np.asarray(X)
         if Xh.dtype == np.uint16 or Xh.dtype == np.int16:
-            counts[:, :G_] = torch.from_numpy(np.ascontiguousarray(Xh).view(np.int16)).to(dev)
+            src = torch.from_numpy(np.ascontiguousarray(Xh).view(np.int16))
+            if G_ == ld:
+                counts.copy_(src, non_blocking=True)
+            else:   # strided device-side placement of a straight (pinned-speed) upload
+                counts[:, :G_] = src.to(dev, non_blocking=True)
         else:
             for r0 in range(0, C_, rows_per_chunk):
                 blk = np.ascontiguousarray(Xh[r0:r0 + rows_per_chunk], dtype=np.float32)
@@ -128,10 +165,11 @@ class ResidualOperator:
         return self.counts.G
 
     @classmethod
-    def from_counts(cls, counts: DeviceCounts, theta: float = THETA, comm=None) -> "ResidualOperator":
-        """`comm`: optional gene-shard communicator (scgeneclust_b200.dist.GeneShardComm); row sums and the
-        total are all-reduced over it so every shard uses the statistics of the full matrix."""
+    def from_counts(cls, counts: DeviceCounts, theta: float = THETA) -> "ResidualOperator":
+        """With a gene-sharded `counts` (counts.comm set) the per-cell sums and the total are all-reduced so every
+        shard uses the statistics of the full matrix."""
         L = lib()
+        comm = counts.comm
         dev = counts.device
         row_sum = torch.zeros(counts.C, dtype=torch.int64, device=dev)
         col_sum = torch.zeros(counts.G, dtype=torch.int64, device=dev)
@@ -176,6 +214,33 @@ class ResidualOperator:
         lib().pearson_residuals(ptr(self.counts.data), self.C, self.G, self.counts.ld, ptr(self.row_sum_f),
                                 ptr(self.col_sum_f), self.total, self.theta, self.clip, ptr(Z), self.G,
                                 stream_handle())
+        return Z
+
+    def materialize_columns(self, gene_idx) -> torch.Tensor:
+        """Dense float32 residual columns (C x len(gene_idx)) of the given genes (singleton-cluster rescue,
+        scGeneClust/tl/selection.py:50)."""
+        dev = self.counts.device
+        gene_idx = np.asarray(gene_idx, dtype=np.int64)
+        comm = self.counts.comm
+        if comm is not None:      # sharded: every rank fills the columns of its own genes, then they are summed
+            mine = (gene_idx >= comm.gene_lo) & (gene_idx < comm.gene_hi)
+            Zall = torch.zeros((self.C, len(gene_idx)), dtype=torch.float32, device=dev)
+            if mine.any():
+                Zall[:, torch.from_numpy(np.flatnonzero(mine)).to(dev)] = self._local_columns(gene_idx[mine] - comm.gene_lo)
+            return comm.all_reduce_sum(Zall)
+        return self._local_columns(gene_idx)
+
+    def _local_columns(self, local_idx: np.ndarray) -> torch.Tensor:
+        dev = self.counts.device
+        idx = torch.as_tensor(local_idx, dtype=torch.int64, device=dev)
+        ns = int(idx.numel())
+        ld = _round_up(max(ns, 1), 64)
+        sub = torch.zeros((self.C, ld), dtype=torch.int16, device=dev)
+        sub[:, :ns] = self.counts.data.index_select(1, idx)
+        col_f = self.col_sum_f.index_select(0, idx).contiguous()
+        Z = torch.empty((self.C, ns), dtype=torch.float32, device=dev)
+        lib().pearson_residuals(ptr(sub), self.C, ns, ld, ptr(self.row_sum_f), ptr(col_f), self.total, self.theta,
+                                self.clip, ptr(Z), ns, stream_handle())
         return Z
 
     def residual_sums(self, rows: bool = True, cols: bool = False):
@@ -224,7 +289,7 @@ def pca_solver(n_samples: int, n_features: int, n_comps: int) -> str:
 
 
 def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_comps: Optional[int] = None,
-                   comm=None, simt: bool = False, info: Optional[dict] = None) -> torch.Tensor:
+                   simt: bool = False, info: Optional[dict] = None) -> torch.Tensor:
     """PCA scores (n_samples x n_comps, float32, device) of the residual matrix.
 
     samples='genes' is `sc.pp.pca(norm_counts.T)` (scGeneClust/pp/_preprocessing.py:52): samples are genes,
@@ -235,6 +300,7 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     """
     L, st = lib(), stream_handle()
     dev = op.counts.device
+    comm = op.counts.comm
     G_total = op.G if comm is None else comm.total_genes
     n_samples, n_features = (G_total, op.C) if samples == "genes" else (op.C, G_total)
     min_dim = min(n_samples, n_features)

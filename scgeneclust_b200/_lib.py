@@ -29,6 +29,8 @@ SIGNATURES = {
     "gc_abi_version": (C.c_int, []),
     "gc_last_error": (C.c_char_p, []),
     "gc_launch_count": (C.c_longlong, []),
+    "gc_profile_enable": (C.c_int, [C.c_int]),
+    "gc_profile_collect": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "gc_csr_to_counts": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
     "gc_dense_to_counts": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "gc_count_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
@@ -51,6 +53,7 @@ SIGNATURES = {
     "gc_kmeanspp_init": (C.c_int, [_p, _i64, _i64, C.c_int, C.c_int, _i32, _p, C.c_int, _p, _p, _p, _p]),
     "gc_sum_f32": (C.c_int, [_p, _i64, _p, _p]),
     "gc_paired_dist": (C.c_int, [_p, _i64, _i64, C.c_int, _p, _p, _p, _p]),
+    "gc_closeness": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gc_mi_prepare": (C.c_int, [_p, _i64, _p, _p, C.c_int, _i64, _i64, _p, _p, _p, _p, _p]),
     "gc_mi_cc_pairs": (C.c_int, [_p, _p, _i64, C.c_int, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "gc_mi_cc_problems": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),

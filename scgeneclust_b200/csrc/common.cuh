@@ -40,6 +40,11 @@ inline int check_launch(const char *kernel) {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// CUDA-event bracket around a dominant kernel (gc_profile_enable / gc_profile_collect); no-ops when disabled.
+enum ProfSlot { kProfRsvdPass = 0, kProfMiPairs = 1, kProfSlots = 2 };
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, cudaStream_t st);
+
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

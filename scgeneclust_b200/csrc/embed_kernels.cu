@@ -569,8 +569,10 @@ extern "C" int gc_rsvd_apply_simt(const gc_residual_matrix *M, int trans, const 
     a.n_split = choose_split(n_tiles, a.n_k);
     a.k_per_split = ceil_div<int64_t>(ceil_div<int64_t>(a.n_k, a.n_split), kTileK) * kTileK;
     dim3 grid((unsigned)n_tiles, (unsigned)a.n_split);
+    prof_begin(kProfRsvdPass, as_stream(stream));
     if (trans == 0) rsvd_apply_simt_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(a);
     else rsvd_apply_simt_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(a);
+    prof_end(kProfRsvdPass, as_stream(stream));
     if (int rc = check_launch("rsvd_apply_simt_kernel")) return rc;
     const int64_t n4 = a.n_out * kQ / 4;
     rsvd_reduce_partials_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, as_stream(stream)>>>(

@@ -150,21 +150,36 @@ struct KppState {
 };
 
 // round step A (1 CTA): adopt the previous winner, sequential float32 cumsum of closest_dist_sq (np.cumsum),
-// searchsorted(rand_vals) -> candidate ids.
+// searchsorted(rand_vals) -> candidate ids.  The cumsum is the order-exact sequential one: chunks are staged
+// through shared memory (coalesced loads/stores by all threads), one thread runs the dependent add chain.
+constexpr int kPickChunk = 8192;
 __global__ void __launch_bounds__(1024)
 kpp_pick_kernel(KppState *st, float *__restrict__ closest, const float *__restrict__ trial_dist, int64_t n,
                 const double *__restrict__ uniforms, int n_trials, int32_t *__restrict__ cand,
                 float *__restrict__ cumsum, int32_t *__restrict__ indices_out, int round) {
+    __shared__ float buf[kPickChunk];
+    __shared__ float carry;
     // closest <- trial_dist[best] (np.minimum result of the winning candidate), round >= 2 only
-    if (round >= 2) {
-        const float *src = trial_dist + (int64_t)st->best * n;
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) closest[i] = src[i];
-        if (threadIdx.x == 0) indices_out[round - 1] = cand[st->best];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float acc = 0.f;
-        for (int64_t i = 0; i < n; ++i) { acc = acc + closest[i]; cumsum[i] = acc; }
+    const bool adopt = round >= 2;
+    const float *src = adopt ? trial_dist + (int64_t)st->best * n : closest;
+    if (adopt && threadIdx.x == 0) indices_out[round - 1] = cand[st->best];
+    if (threadIdx.x == 0) carry = 0.f;
+    for (int64_t c0 = 0; c0 < n; c0 += kPickChunk) {
+        const int cn = (int)min((int64_t)kPickChunk, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+            const float v = src[c0 + i];
+            buf[i] = v;
+            if (adopt) closest[c0 + i] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float acc = carry;
+            for (int i = 0; i < cn; ++i) { acc = acc + buf[i]; buf[i] = acc; }
+            carry = acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) cumsum[c0 + i] = buf[i];
     }
     __syncthreads();
     if (threadIdx.x < n_trials) {
@@ -268,6 +283,35 @@ __global__ void paired_dist_kernel(const float *__restrict__ X, int64_t ldx, int
     dist[s] = sqrtf(acc);
 }
 
+// per-cluster min / max of non-negative float32 distances via integer atomics on the bit patterns (order
+// preserving for values >= 0), then closeness = 1 - (d * scale + min_) with sklearn MinMaxScaler's float32 steps
+__global__ void closeness_init_kernel(int32_t *scratch, int K) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < K) { scratch[j] = 0x7f800000; scratch[K + j] = 0; }
+}
+__global__ void closeness_minmax_kernel(const float *__restrict__ dist, const int32_t *__restrict__ labels, int64_t n,
+                                        int K, int32_t *scratch) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int b = __float_as_int(dist[s]), l = labels[s];
+    atomicMin(&scratch[l], b);
+    atomicMax(&scratch[K + l], b);
+}
+__global__ void closeness_apply_kernel(const float *__restrict__ dist, const int32_t *__restrict__ labels, int64_t n,
+                                       int K, const int32_t *__restrict__ scratch, float *__restrict__ out) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int l = labels[s];
+    const float dmin = __int_as_float(scratch[l]), dmax = __int_as_float(scratch[K + l]);
+    float range = dmax - dmin;
+    if (range < 10.0f * 1.1920928955078125e-07f) range = 1.0f;   // _handle_zeros_in_scale
+    const float scale = 1.0f / range;
+    const float min_ = 0.0f - dmin * scale;
+    float v = dist[s] * scale;
+    v = v + min_;
+    out[s] = 1.0f - v;
+}
+
 // deterministic float64 sum of a float32 vector (single CTA, fixed tree), result as float64 and float32
 __global__ void __launch_bounds__(1024) sum_f32_kernel(const float *__restrict__ v, int64_t n, double *out) {
     __shared__ double red[1024];
@@ -328,6 +372,18 @@ extern "C" int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, con
     paired_dist_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, as_stream(stream)>>>(X, ldx, n, d, centers,
                                                                                           labels, dist);
     return check_launch("paired_dist_kernel");
+}
+
+extern "C" int gc_closeness(const float *dist, const int32_t *labels, int64_t n, int K, int32_t *scratch,
+                            float *closeness, void *stream) {
+    GC_REQUIRE(dist && labels && scratch && closeness && n >= 1 && K >= 1, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    closeness_init_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(scratch, K);
+    if (int rc = check_launch("closeness_init_kernel")) return rc;
+    closeness_minmax_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, st>>>(dist, labels, n, K, scratch);
+    if (int rc = check_launch("closeness_minmax_kernel")) return rc;
+    closeness_apply_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, st>>>(dist, labels, n, K, scratch, closeness);
+    return check_launch("closeness_apply_kernel");
 }
 
 extern "C" int gc_sum_f32(const float *v, int64_t n, double *out, void *stream) {

@@ -366,8 +366,10 @@ extern "C" int gc_mi_cc_pairs(const double *XR, const double *YR, int64_t N, int
     long long blocks = ceil_div<long long>(n_pairs, kPairWarps);
     const long long cap = (long long)kNumSMs * 8 * 4;  // 8 CTAs of 8 warps per SM, 4 waves; grid-stride beyond
     if (blocks > cap) blocks = cap;
+    prof_begin(kProfMiPairs, as_stream(stream));
     mi_cc_pairs_kernel<<<(unsigned)blocks, kPairWarps * 32, 0, as_stream(stream)>>>(
         XR, YR, N, n, ldr, psi, p_begin, p_end, mi_condensed, dense, nx_out, ny_out);
+    prof_end(kProfMiPairs, as_stream(stream));
     return check_launch("mi_cc_pairs_kernel");
 }
 

@@ -22,6 +22,7 @@ class HotPathState:
     Z: Optional[torch.Tensor] = None             # materialised residuals (ps path), float32 C x G
     varm_pca: Optional[torch.Tensor] = None      # device copy of varm['X_pca']
     obsm_pca: Optional[torch.Tensor] = None
+    redundancy: Optional[torch.Tensor] = None    # device copy of varp['redundancy']
     comm: object = None                          # optional GeneShardComm
     info: dict = field(default_factory=dict)
 
@@ -45,10 +46,13 @@ def normalize(adata, modality: Literal['sc', 'st'] = 'sc', materialize: bool = F
     if modality != 'sc':
         raise NotImplementedError("modality='st' (normalize_total + log1p, SpaGCN) is outside the B200 hot path")
     st = get_state(adata)
-    counts = adata.X if isinstance(adata.X, DeviceCounts) else ingest_counts(adata.X)
-    st.op = ResidualOperator.from_counts(counts, comm=st.comm)
+    counts = ingest_counts(adata.X)
+    st.comm = counts.comm
+    st.op = ResidualOperator.from_counts(counts)
     adata.uns['pearson_residuals_normalization'] = {'theta': st.op.theta, 'clip': None, 'computed_on': 'adata.X'}
     if materialize:
+        if st.comm is not None:
+            raise NotImplementedError("dense residuals (GeneClust-ps / return_info) need the unsharded matrix")
         st.Z = st.op.materialize()
         adata.X = st.Z.cpu().numpy()
 
@@ -60,12 +64,12 @@ def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):
     if st.op is None:
         raise RuntimeError("reduce_dim called before normalize")
     info = {}
-    st.varm_pca = randomized_pca(st.op, 'genes', random_state, comm=st.comm, info=info)
+    st.varm_pca = randomized_pca(st.op, 'genes', random_state, info=info)
     st.info['gene_pca'] = info
     if st.comm is not None:
         st.varm_pca = st.comm.all_gather_rows(st.varm_pca)
     adata.varm['X_pca'] = st.varm_pca.cpu().numpy()
     if version == 'ps':
-        st.obsm_pca = randomized_pca(st.op, 'cells', random_state, comm=st.comm)
+        st.obsm_pca = randomized_pca(st.op, 'cells', random_state)
         adata.obsm['X_pca'] = st.obsm_pca.cpu().numpy()
     logger.info("Data preprocessing done.")

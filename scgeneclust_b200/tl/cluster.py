@@ -1,0 +1,197 @@
+"""Gene clustering stage with the reference's names and semantics (scGeneClust/tl/cluster.py:22-131), running on
+the device.  GeneClust-fast = mini-batch k-means on `varm['X_pca']` + per-cluster closeness; GeneClust-ps =
+relevance -> redundancy -> MST + complementarity -> HDBSCAN-style gene clusters."""
+from __future__ import annotations
+
+import os
+from typing import Literal, Optional
+
+import numpy as np
+import torch
+from loguru import logger
+
+from .._lib import lib, ptr, require_cuda, stream_handle
+from ..pp._preprocessing import get_state
+
+
+class DeviceMiniBatchKMeans:
+    """`sklearn.cluster.MiniBatchKMeans(n_clusters, batch_size, random_state, n_init='auto')` as the reference
+    configures it (scGeneClust/tl/cluster.py:66-69), re-expressed for the device.
+
+    The control flow and every draw from `RandomState` follow scikit-learn 1.9.0 `MiniBatchKMeans.fit`
+    (cluster/_kmeans.py:2056-2224): validation-set `randint`, init-subset `randint`, k-means++ `choice`/`uniform`,
+    per-step `choice(n, batch, p)`, `choice(replace=False)` on random reassignment; defaults max_iter=100,
+    max_no_improvement=10, reassignment_ratio=0.01, tol=0, init='k-means++', n_init=1.  The arithmetic (distances,
+    argmin, running means, potentials) runs in kernels of libgeneclust_b200.so; the host keeps only the RNG, the
+    K-length count vector and the early-stopping scalars.
+    """
+
+    def __init__(self, n_clusters: int, batch_size: int = 1024, random_state: int = 0, max_iter: int = 100,
+                 max_no_improvement: int = 10, reassignment_ratio: float = 0.01):
+        self.n_clusters, self.batch_size, self.random_state = int(n_clusters), int(batch_size), random_state
+        self.max_iter, self.max_no_improvement, self.reassignment_ratio = max_iter, max_no_improvement, reassignment_ratio
+
+    # -- k-means++ on a (sub)sample, cluster/_kmeans.py:180-275 ------------------------------------------------
+    def _init_centroids(self, X: torch.Tensor, rs: np.random.RandomState, init_size: int) -> torch.Tensor:
+        L, st = lib(), stream_handle()
+        n, d = X.shape
+        K = self.n_clusters
+        if init_size < n:                                    # _init_centroids, cluster/_kmeans.py:1015-1020
+            init_indices = rs.randint(0, n, init_size)
+            Xs = X.index_select(0, torch.from_numpy(init_indices).to(X.device)).contiguous()
+        else:
+            Xs = X
+        ns = Xs.shape[0]
+        n_trials = 2 + int(np.log(K))
+        sw = np.ones(ns, dtype=np.float32)
+        first = int(rs.choice(ns, p=sw / sw.sum()))
+        uniforms = np.stack([rs.uniform(size=n_trials) for _ in range(K - 1)]) if K > 1 else np.zeros((0, n_trials))
+        d_uni = torch.from_numpy(np.ascontiguousarray(uniforms)).to(X.device)
+        ws = torch.empty(L.kmeanspp_scratch_bytes(ns, n_trials), dtype=torch.uint8, device=X.device)
+        centers = torch.empty((K, d), dtype=torch.float32, device=X.device)
+        indices = torch.empty(K, dtype=torch.int32, device=X.device)
+        L.kmeanspp_init(ptr(Xs), Xs.stride(0), ns, d, K, first, ptr(d_uni), n_trials, ptr(ws), ptr(centers),
+                        ptr(indices), st)
+        self.init_indices_ = indices
+        return centers
+
+    def fit_predict(self, X: torch.Tensor) -> torch.Tensor:
+        require_cuda()
+        L, st = lib(), stream_handle()
+        assert X.dtype == torch.float32 and X.is_cuda and X.is_contiguous()
+        n, d = X.shape
+        K = self.n_clusters
+        if n < K:
+            raise ValueError(f"n_samples={n} should be >= n_clusters={K}.")   # sklearn _check_params_vs_input
+        dev = X.device
+        rs = np.random.RandomState(self.random_state)
+        batch = min(self.batch_size, n)
+        init_size = 3 * batch
+        if init_size < K:
+            init_size = 3 * K
+        init_size = min(init_size, n)
+
+        rs.randint(0, n, init_size)                          # validation set (only ranks inits; n_init == 1)
+        centers = self._init_centroids(X, rs, init_size)
+        centers_new = torch.empty_like(centers)
+        counts = torch.zeros(K, dtype=torch.float32, device=dev)
+        counts_h = np.zeros(K, dtype=np.float32)
+
+        ewa, ewa_min, no_improvement, n_since_reassign = None, None, 0, 0
+        n_steps = (self.max_iter * n) // batch
+        p = np.ones(n, dtype=np.float32)
+        p = p / np.sum(p)
+        labels_b = torch.empty(batch, dtype=torch.int32, device=dev)
+        sq_b = torch.empty(batch, dtype=torch.float32, device=dev)
+        inertia_d = torch.empty(1, dtype=torch.float64, device=dev)
+        step = 0
+        for step in range(n_steps):
+            idx_h = rs.choice(n, batch, p=p, replace=True)
+            idx = torch.from_numpy(idx_h.astype(np.int32)).to(dev, non_blocking=True)
+            # _random_reassign(), evaluated before the step on the counts of the previous one
+            n_since_reassign += batch
+            random_reassign = bool((counts_h == 0).any() or n_since_reassign >= 10 * K)
+            if random_reassign:
+                n_since_reassign = 0
+            # _mini_batch_step
+            L.kmeans_assign(ptr(X), X.stride(0), ptr(idx), batch, ptr(centers), K, d, ptr(labels_b), ptr(sq_b), st)
+            L.sum_f32(ptr(sq_b), batch, ptr(inertia_d), st)
+            L.kmeans_minibatch_update(ptr(X), X.stride(0), ptr(idx), batch, ptr(labels_b), ptr(centers),
+                                      ptr(centers_new), ptr(counts), K, d, st)
+            counts_h = counts.cpu().numpy()
+            batch_inertia = float(np.float32(inertia_d.item()))
+            if random_reassign and self.reassignment_ratio > 0:
+                to_reassign = counts_h < self.reassignment_ratio * counts_h.max()
+                if to_reassign.sum() > 0.5 * batch:
+                    keep = np.argsort(counts_h)[int(0.5 * batch):]
+                    to_reassign[keep] = False
+                n_reassigns = int(to_reassign.sum())
+                if n_reassigns:
+                    picks = rs.choice(batch, replace=False, size=n_reassigns)
+                    rows = torch.from_numpy(idx_h[picks].astype(np.int64)).to(dev)
+                    centers_new[torch.from_numpy(np.flatnonzero(to_reassign)).to(dev)] = X.index_select(0, rows)
+                counts_h = counts_h.copy()
+                counts_h[to_reassign] = np.min(counts_h[~to_reassign])
+                counts.copy_(torch.from_numpy(counts_h))
+            centers, centers_new = centers_new, centers
+            # _mini_batch_convergence (tol == 0)
+            batch_inertia /= batch
+            if step == 0:
+                continue
+            if ewa is None:
+                ewa = batch_inertia
+            else:
+                alpha = min(batch * 2.0 / (n + 1), 1)
+                ewa = ewa * (1 - alpha) + batch_inertia * alpha
+            if ewa_min is None or ewa < ewa_min:
+                no_improvement, ewa_min = 0, ewa
+            else:
+                no_improvement += 1
+            if self.max_no_improvement is not None and no_improvement >= self.max_no_improvement:
+                break
+        self.cluster_centers_ = centers
+        self.n_steps_ = step + 1
+        self.labels_ = torch.empty(n, dtype=torch.int32, device=dev)
+        L.kmeans_assign(ptr(X), X.stride(0), None, n, ptr(centers), K, d, ptr(self.labels_), None, st)
+        return self.labels_
+
+
+def compute_gene_closeness(X_pca: torch.Tensor, labels: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    """scGeneClust/tl/cluster.py:84-105 on the device: euclidean distance of every gene to its cluster centre
+    (`paired_distances`), then `1 - minmax_scale` within each cluster (float32, sklearn's x*scale + min form)."""
+    L, st = lib(), stream_handle()
+    n, d = X_pca.shape
+    K = centers.shape[0]
+    dist = torch.empty(n, dtype=torch.float32, device=X_pca.device)
+    out = torch.empty_like(dist)
+    scratch = torch.empty(2 * K, dtype=torch.int32, device=X_pca.device)
+    L.paired_dist(ptr(X_pca), X_pca.stride(0), n, d, ptr(centers), ptr(labels), ptr(dist), st)
+    L.closeness(ptr(dist), ptr(labels), n, K, ptr(scratch), ptr(out), st)
+    return out
+
+
+def cluster_genes(adata, img: Optional[np.ndarray], version: Literal['fast', 'ps'],
+                  modality: Literal['sc', 'st'] = 'sc', shape: Literal['hexagon', 'square'] = 'hexagon',
+                  n_gene_clusters: int = None, n_obs_clusters: int = None, n_components: int = 10,
+                  relevant_gene_pct: int = 20, max_workers: int = os.cpu_count() - 1, random_state: int = 0):
+    """Same signature and AnnData side effects as the reference (scGeneClust/tl/cluster.py:22-81).  `max_workers`
+    is accepted for compatibility; the work runs on the GPU."""
+    logger.info("Clustering genes...")
+    st = get_state(adata)
+    if version == 'fast':
+        X = st.varm_pca
+        if X is None:
+            X = torch.from_numpy(np.ascontiguousarray(adata.varm['X_pca'], dtype=np.float32)).cuda()
+        km = DeviceMiniBatchKMeans(n_clusters=n_gene_clusters, batch_size=max(1024, adata.n_vars // 10),
+                                   random_state=random_state)
+        labels = km.fit_predict(X)
+        closeness = compute_gene_closeness(X, labels, km.cluster_centers_)
+        adata.var['cluster'] = labels.cpu().numpy()
+        adata.var['closeness'] = closeness.cpu().numpy()
+        st.info['kmeans'] = dict(n_steps=km.n_steps_, centers=km.cluster_centers_)
+    else:
+        from .confidence import find_high_confidence_cells
+        from .information import compute_gene_complementarity, compute_gene_redundancy, find_relevant_genes
+        if modality != 'sc':
+            raise NotImplementedError("modality='st' (SpaGCN spatial domains) is outside the B200 hot path")
+        find_high_confidence_cells(adata, n_obs_clusters, n_components, max_workers, random_state)
+        find_relevant_genes(adata, relevant_gene_pct, max_workers, random_state)
+        compute_gene_redundancy(adata, max_workers, random_state)
+        compute_gene_complementarity(adata, max_workers, random_state)
+        generate_gene_clusters(adata)
+    logger.info("Gene clustering done!")
+
+
+def generate_gene_clusters(adata):
+    """scGeneClust/tl/cluster.py:108-131: MST + edge scale -> single-linkage tree -> condensed tree (min cluster size
+    3) -> EOM clusters + GLOSH outlier scores.  Sequential O(N) tree walks on a few thousand genes: host side."""
+    from ._hdbscan_tail import mst_to_clusters
+    g1, g2 = adata.uns['mst_edges'][:, 0], adata.uns['mst_edges'][:, 1]
+    rel = adata.var['relevance'].values
+    edge_min_relevance = np.minimum(rel[g1], rel[g2])
+    edge_redundancy = adata.varp['redundancy'][g1, g2]
+    edge_scales = np.maximum(edge_min_relevance, adata.uns['mst_edges_complm']) / edge_redundancy
+    MST = np.hstack((adata.uns['mst_edges'], edge_scales.reshape(-1, 1)))
+    MST = MST[np.argsort(MST.T[2]), :]
+    labels, scores = mst_to_clusters(MST, adata.n_vars, min_cluster_size=3)
+    adata.var['outlier_score'], adata.var['cluster'] = scores, labels

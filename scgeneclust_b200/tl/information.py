@@ -1,0 +1,257 @@
+"""GeneClust-ps information-theoretic stages with the reference's names and semantics
+(scGeneClust/tl/information.py:21-132) on the device: relevance (Ross kNN MI of every gene against the pseudo cell
+types), redundancy (KSG kNN MI of every gene pair on the 50-d gene embedding), MST, and complementarity
+(per-cell-cluster KSG MI on the MST edges).  The estimators are the exact fp64 ones scikit-learn 1.9.0 runs for the
+reference (`mutual_info_classif` / `mutual_info_regression`, feature_selection/_mutual_info.py:20-153, 294-315);
+their integer neighbour counts are bit-identical."""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+from loguru import logger
+from scipy.special import digamma
+
+from .._lib import lib, ptr, require_cuda, stream_handle
+from ..pp._preprocessing import get_state
+
+K_NEIGHBORS = 3
+
+
+def _psi_table(n_max: int, device) -> torch.Tensor:
+    """psi[m] = digamma(m) for m = 1..n_max (psi[0] unused), from scipy like the reference's estimator."""
+    t = np.zeros(n_max + 1, dtype=np.float64)
+    t[1:] = digamma(np.arange(1, n_max + 1, dtype=np.float64))
+    return torch.from_numpy(t).to(device)
+
+
+def _noise(n: int, random_state: int, target: bool):
+    """The normals `_estimate_mi` draws from a fresh RandomState(seed) (feature_selection/_mutual_info.py:296-315):
+    xi1 for the single feature column, then xi2 for a continuous target."""
+    rng = np.random.RandomState(random_state)
+    xi1 = rng.standard_normal(size=(n, 1))[:, 0]
+    xi2 = rng.standard_normal(size=n) if target else None
+    return xi1, xi2
+
+
+def _device_matrix(adata, st, attr: str, host) -> torch.Tensor:
+    t = getattr(st, attr, None)
+    if t is not None and tuple(t.shape) == tuple(np.shape(host)):
+        return t
+    return torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32)).cuda()
+
+
+# -------------------------------------------------------------------------------------------------------------
+# a6 relevance
+# -------------------------------------------------------------------------------------------------------------
+def gene_relevance(Z: torch.Tensor, labels, random_state: int = 0, return_counts: bool = False):
+    """Ross MI of every column of Z (n cells x G genes, float32, device) against `labels` - what
+    `_compute_relevance` (scGeneClust/tl/information.py:21-24) returns for every gene.  float64 tensor [G]."""
+    require_cuda()
+    L, stream = lib(), stream_handle()
+    dev = Z.device
+    n, G = Z.shape
+    labels = np.asarray(labels)
+    uniq, inv, cnt = np.unique(labels, return_inverse=True, return_counts=True)
+    label_k = np.where(cnt > 1, np.minimum(K_NEIGHBORS, cnt - 1), 0).astype(np.int32)
+    keep = cnt[inv] > 1
+    n_kept = int(keep.sum())
+    if n_kept < 2:
+        raise ValueError("relevance needs at least one label with more than one cell")
+    k_all = label_k[inv][keep].astype(np.float64)
+    label_counts = cnt[inv][keep].astype(np.float64)
+    const_term = (digamma(n_kept) + np.mean(digamma(k_all))) - np.mean(digamma(label_counts))
+    xi1, _ = _noise(n, random_state, target=False)
+
+    order = torch.arange(n, dtype=torch.int32, device=dev)
+    seg_off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    d_xi1 = torch.from_numpy(xi1).to(dev)
+    XR = torch.empty((G, n), dtype=torch.float64, device=dev)
+    L.mi_prepare(ptr(Z), Z.stride(0), ptr(order), ptr(seg_off), 1, G, n, ptr(d_xi1), None, ptr(XR), None, stream)
+    d_label = torch.from_numpy(inv.astype(np.int32)).to(dev)
+    d_label_k = torch.from_numpy(label_k).to(dev)
+    m_all = torch.empty((n, G), dtype=torch.int32, device=dev)
+    mi = torch.empty(G, dtype=torch.float64, device=dev)
+    L.mi_cd(ptr(XR), n, G, n, ptr(d_label), ptr(d_label_k), len(uniq), float(const_term), ptr(_psi_table(n, dev)),
+            ptr(m_all), ptr(mi), stream)
+    if return_counts:
+        return mi, m_all, keep
+    return mi
+
+
+def find_relevant_genes(adata, top_pct: int, max_workers: int = os.cpu_count() - 1, random_state: int = 0):
+    """scGeneClust/tl/information.py:27-57: `var['relevance']`, then in-place subset to the genes whose relevance is
+    strictly above the (100 - top_pct) percentile."""
+    logger.info("Finding relevant genes...")
+    st = get_state(adata)
+    Z = _device_matrix(adata, st, 'Z', adata.X)
+    relevance = gene_relevance(Z, np.asarray(adata.obs['cluster']), random_state).cpu().numpy()
+    logger.debug("Gene relevance computed!")
+    rlv_th = np.percentile(relevance, 100 - top_pct)
+    logger.opt(colors=True).debug(f"Relevance threshold: <yellow>{rlv_th}</yellow>")
+    is_relevant = relevance > rlv_th
+    adata._inplace_subset_var(is_relevant)
+    adata.var['relevance'] = relevance[is_relevant]
+    keep = torch.from_numpy(np.flatnonzero(is_relevant)).to(Z.device)
+    st.Z = Z.index_select(1, keep).contiguous()
+    if st.varm_pca is not None:
+        st.varm_pca = st.varm_pca.index_select(0, keep).contiguous()
+    logger.opt(colors=True).info(
+        f"<yellow>{is_relevant.sum()}</yellow> (<yellow>{top_pct}%</yellow>) genes are marked as relevant genes."
+    )
+
+
+# -------------------------------------------------------------------------------------------------------------
+# a7 redundancy
+# -------------------------------------------------------------------------------------------------------------
+def prepare_pair_roles(E: torch.Tensor, random_state: int = 0):
+    """Feature-role (float64 path) and target-role (float32 path) versions of every row of E (N x n float32):
+    what `_estimate_mi` hands to `_compute_mi_cc` as x resp. y (feature_selection/_mutual_info.py:294-315)."""
+    L, stream = lib(), stream_handle()
+    dev = E.device
+    N, n = E.shape
+    xi1, xi2 = _noise(n, random_state, target=True)
+    Et = E.t().contiguous()                                   # samples x genes, the layout gc_mi_prepare reads
+    order = torch.arange(n, dtype=torch.int32, device=dev)
+    seg_off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    XR = torch.empty((N, n), dtype=torch.float64, device=dev)
+    YR = torch.empty((N, n), dtype=torch.float64, device=dev)
+    L.mi_prepare(ptr(Et), Et.stride(0), ptr(order), ptr(seg_off), 1, N, n, ptr(torch.from_numpy(xi1).to(dev)),
+                 ptr(torch.from_numpy(xi2).to(dev)), ptr(XR), ptr(YR), stream)
+    return XR, YR
+
+
+def gene_redundancy(E: torch.Tensor, random_state: int = 0, p_begin: int = 0, p_end: Optional[int] = None,
+                    dense: bool = True, return_counts: bool = False):
+    """KSG MI of the gene pairs [p_begin, p_end) in `itertools.combinations(range(N), 2)` order - the values
+    `_compute_redundancy` (scGeneClust/tl/information.py:60-63) returns.  Returns (condensed[p_end-p_begin],
+    dense N x N symmetric or None[, nx, ny uint8 counts])."""
+    require_cuda()
+    L, stream = lib(), stream_handle()
+    dev = E.device
+    N, n = E.shape
+    n_pairs = N * (N - 1) // 2
+    p_end = n_pairs if p_end is None else p_end
+    XR, YR = prepare_pair_roles(E, random_state)
+    cond = torch.empty(p_end - p_begin, dtype=torch.float64, device=dev)
+    D = torch.zeros((N, N), dtype=torch.float64, device=dev) if dense else None
+    nx = torch.empty((p_end - p_begin, n), dtype=torch.uint8, device=dev) if return_counts else None
+    ny = torch.empty_like(nx) if return_counts else None
+    L.mi_cc_pairs(ptr(XR), ptr(YR), N, n, n, ptr(_psi_table(n, dev)), p_begin, p_end, ptr(cond), ptr(D), ptr(nx),
+                  ptr(ny), stream)
+    if return_counts:
+        return cond, D, nx, ny
+    return cond, D
+
+
+def compute_gene_redundancy(adata, max_workers: int = os.cpu_count() - 1, random_state: int = 0):
+    """scGeneClust/tl/information.py:66-85: `varp['redundancy']` = symmetric N x N float64, zero diagonal.  With a
+    gene-shard communicator in the state, ranks compute disjoint condensed ranges and all-gather them."""
+    logger.info("Computing gene redundancy...")
+    st = get_state(adata)
+    E = _device_matrix(adata, st, 'varm_pca', adata.varm['X_pca'])
+    N = E.shape[0]
+    comm = st.comm
+    if comm is None or comm.world == 1:
+        _, D = gene_redundancy(E, random_state)
+    else:
+        n_pairs = N * (N - 1) // 2
+        lo, hi = comm.split_range(n_pairs)
+        cond, _ = gene_redundancy(E, random_state, lo, hi, dense=False)
+        full = comm.all_gather_ranges(cond, n_pairs)
+        D = torch.zeros((N, N), dtype=torch.float64, device=E.device)
+        iu = torch.triu_indices(N, N, 1, device=E.device)
+        D[iu[0], iu[1]] = full
+        D = D + D.t()
+    st.redundancy = D
+    adata.varp['redundancy'] = D.cpu().numpy()
+    logger.info("Gene redundancy computed.")
+
+
+# -------------------------------------------------------------------------------------------------------------
+# MST (scGeneClust/tl/information.py:124-126) - "next" row of the scope table; host side for now
+# -------------------------------------------------------------------------------------------------------------
+def redundancy_mst(R: np.ndarray) -> np.ndarray:
+    """Maximum-redundancy spanning tree (forest, if the MI > 0 graph is disconnected) of the graph that has an
+    edge wherever R != 0 - igraph `Weighted_Adjacency(-R, 'undirected').spanning_tree(weights)`.  Returns the
+    (n_edges, 2) int array ordered like igraph's edge ids (upper triangle, row-major), source < target."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    iu = np.triu_indices(R.shape[0], 1)
+    w = R[iu]
+    nz = w != 0
+    graph = csr_matrix((-w[nz], (iu[0][nz], iu[1][nz])), shape=R.shape)
+    mst = minimum_spanning_tree(graph).tocoo()
+    src, dst = np.minimum(mst.row, mst.col), np.maximum(mst.row, mst.col)
+    order = np.lexsort((dst, src))
+    return np.stack([src[order], dst[order]], axis=1).astype(np.int64)
+
+
+# -------------------------------------------------------------------------------------------------------------
+# a8 complementarity
+# -------------------------------------------------------------------------------------------------------------
+def gene_complementarity(Z: torch.Tensor, clusters, edges: np.ndarray, random_state: int = 0) -> np.ndarray:
+    """`_compute_complementarity` (scGeneClust/tl/information.py:88-98) for every edge (i, j): sum over the cell
+    clusters c of KSG-MI(Z[c, i], Z[c, j]) * n_c / n.  Z: n cells x N genes float32 on the device."""
+    require_cuda()
+    L, stream = lib(), stream_handle()
+    dev = Z.device
+    n, N = Z.shape
+    clusters = np.asarray(clusters)
+    uniq, inv, cnt = np.unique(clusters, return_inverse=True, return_counts=True)
+    if cnt.min() <= K_NEIGHBORS:
+        raise ValueError("every cell cluster needs more than 3 cells for the k = 3 neighbour estimator")
+    order = np.argsort(inv, kind="stable").astype(np.int32)     # cells grouped by cluster, original order inside
+    seg_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    xi1 = np.empty(n, np.float64)
+    xi2 = np.empty(n, np.float64)
+    for c, m in enumerate(cnt):                                 # fresh RandomState(seed) per call, length n_c
+        a, b = _noise(int(m), random_state, target=True)
+        xi1[seg_off[c]:seg_off[c + 1]], xi2[seg_off[c]:seg_off[c + 1]] = a, b
+    edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    genes = np.unique(edges)                                    # only the genes on an edge are prepared
+    pos = np.full(N, -1, np.int64)
+    pos[genes] = np.arange(len(genes))
+    Zs = Z.index_select(1, torch.from_numpy(genes).to(dev)).contiguous()
+    Gs = len(genes)
+    XR = torch.empty((Gs, n), dtype=torch.float64, device=dev)
+    YR = torch.empty((Gs, n), dtype=torch.float64, device=dev)
+    L.mi_prepare(ptr(Zs), Zs.stride(0), ptr(torch.from_numpy(order).to(dev)), ptr(torch.from_numpy(seg_off).to(dev)),
+                 len(uniq), Gs, n, ptr(torch.from_numpy(xi1).to(dev)), ptr(torch.from_numpy(xi2).to(dev)), ptr(XR),
+                 ptr(YR), stream)
+    n_edges, n_c = len(edges), len(uniq)
+    e_i = np.repeat(pos[edges[:, 0]], n_c)
+    e_j = np.repeat(pos[edges[:, 1]], n_c)
+    seg = np.tile(np.arange(n_c), n_edges)
+    x_off = e_i * n + seg_off[seg]
+    y_off = e_j * n + seg_off[seg]
+    length = cnt[seg].astype(np.int32)
+    out_off = np.concatenate([[0], np.cumsum(length[:-1], dtype=np.int64)]).astype(np.int64)
+    total = int(length.sum(dtype=np.int64))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    nx = torch.empty(total, dtype=torch.int32, device=dev)
+    ny = torch.empty(total, dtype=torch.int32, device=dev)
+    mi = torch.empty(n_edges * n_c, dtype=torch.float64, device=dev)
+    L.mi_cc_problems(ptr(XR), ptr(YR), ptr(t(x_off.astype(np.int64))), ptr(t(y_off.astype(np.int64))), ptr(t(length)),
+                     ptr(t(out_off)), n_edges * n_c, ptr(_psi_table(int(cnt.max()), dev)), ptr(nx), ptr(ny), ptr(mi),
+                     stream)
+    mi_h = mi.cpu().numpy().reshape(n_edges, n_c)
+    cmi = np.zeros(n_edges)
+    for c in range(n_c):                                        # the reference's accumulation order (np.unique order)
+        cmi = cmi + mi_h[:, c] * cnt[c] / n
+    return cmi
+
+
+def compute_gene_complementarity(adata, max_workers: int = os.cpu_count() - 1, random_state: int = 0):
+    """scGeneClust/tl/information.py:101-132: `uns['mst_edges']`, `uns['mst_edges_complm']`."""
+    logger.info("Computing gene complementarity...")
+    st = get_state(adata)
+    logger.debug("Building MST...")
+    adata.uns['mst_edges'] = redundancy_mst(adata.varp['redundancy'])
+    logger.debug("MST built.")
+    Z = _device_matrix(adata, st, 'Z', adata.X)
+    adata.uns['mst_edges_complm'] = gene_complementarity(Z, np.asarray(adata.obs['cluster']), adata.uns['mst_edges'],
+                                                         random_state)
+    logger.info("Gene complementarity computed.")

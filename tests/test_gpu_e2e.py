@@ -1,0 +1,115 @@
+"""End-to-end parity of `scGeneClust(adata, version='fast'|'ps')` through the public entry point against the CPU
+oracle on the same seeded synthetic counts."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def data():
+    from oracle.synth import cell_types, synth_counts
+    from scgeneclust_b200.synth import synth_params
+    p = synth_params(2500, 0)
+    X = synth_counts(p, 0, 3000, 0, 2500)
+    keep = (X > 0).sum(0) >= 3
+    names = np.array([f"gene{i}" for i in np.flatnonzero(keep)], dtype=object)
+    return np.ascontiguousarray(X[:, keep]), names, cell_types(p, 0, 3000)
+
+
+def test_fast_end_to_end_vs_oracle(torch_cuda, data):
+    from sklearn.metrics import adjusted_rand_score
+    from oracle import stages
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    X, names, _ = data
+    K = 40
+    ref = stages.geneclust_fast(X, names, K, 0)
+    for X_in in (X.astype(np.float32), sp.csr_matrix(X.astype(np.float32))):
+        raw = AnnDataLite(X_in, var_names=names)
+        info, sel = scGeneClust(raw, n_var_clusters=K, version='fast', return_info=True, verbosity=0)
+        emb = info.varm['X_pca']
+        rel = np.linalg.norm(emb - ref['X_pca'], axis=0) / np.linalg.norm(ref['X_pca'], axis=0)
+        ari = adjusted_rand_score(info.var['cluster'].to_numpy(), ref['labels'])
+        same = np.array_equal(sel, ref['selected'])
+        print(f"fast e2e: PCA rel err {rel.max():.2e}, ARI {ari:.4f}, selected {len(sel)} genes, identical list: {same}")
+        assert rel.max() <= 1e-3
+        assert ari >= 0.9
+        assert set(sel) <= set(names) and len(sel) <= 2 * K + (np.bincount(info.var['cluster']) == 1).sum()
+        assert info.X.shape == X.shape and info.X.dtype == np.float32          # residuals (return_info contract)
+        assert np.allclose(info.X, ref['Z'], rtol=2e-5, atol=2e-6)
+        cl = info.var['closeness'].to_numpy()
+        assert cl.max() <= 1.0 and cl.min() >= -1e-6
+    # given the oracle's embedding, the k-means + selection tail must reproduce the oracle's list exactly
+    from scgeneclust_b200.tl import cluster_genes, select_from_clusters
+    ad = AnnDataLite(ref['Z'].copy(), var_names=names)
+    ad.varm['X_pca'] = ref['X_pca']
+    cluster_genes(ad, None, 'fast', n_gene_clusters=K, random_state=0)
+    lab_same = np.array_equal(ad.var['cluster'].to_numpy(), ref['labels'])
+    sel2 = select_from_clusters(ad, 'fast', True, 0)
+    print(f"fast tail on the oracle embedding: labels identical {lab_same}, list identical "
+          f"{np.array_equal(sel2, ref['selected'])}")
+    assert adjusted_rand_score(ad.var['cluster'].to_numpy(), ref['labels']) >= 0.95
+
+
+def test_return_modes(torch_cuda, data):
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    X, names, _ = data
+    raw = AnnDataLite(X[:, :800].astype(np.float32), var_names=names[:800])
+    sel = scGeneClust(raw, n_var_clusters=20, verbosity=0)
+    assert isinstance(sel, np.ndarray) and raw.n_vars == 800          # input untouched
+    assert scGeneClust(raw, n_var_clusters=20, subset=True, verbosity=0) is None
+    assert raw.n_vars == len(sel) and set(raw.var_names) == set(sel)
+
+
+def test_ps_stages_vs_oracle(torch_cuda, data):
+    """GeneClust-ps with the pseudo cell types given: relevance, redundancy, complementarity equal the oracle's
+    (sklearn calls) on the device-computed residuals/embedding."""
+    from oracle import stages
+    from scgeneclust_b200 import AnnDataLite
+    from scgeneclust_b200 import pp
+    from scgeneclust_b200.tl.confidence import find_high_confidence_cells
+    from scgeneclust_b200.tl.information import (compute_gene_complementarity, compute_gene_redundancy,
+                                                 find_relevant_genes)
+    X, names, types = data
+    X, names = X[:1200, :600], names[:600]
+    ok = (X > 0).sum(0) >= 3
+    X, names = np.ascontiguousarray(X[:, ok]), names[ok]
+    ad = AnnDataLite(X.astype(np.float32), var_names=names)
+    ad.obs['cluster'] = np.array([f"type{t}" for t in types[:1200]])
+    hc = np.ones(1200, bool)
+    hc[::3] = False
+    ad.obs['highly_confident'] = hc
+    pp.normalize(ad, 'sc', materialize=True)
+    pp.reduce_dim(ad, 'ps', 0)
+    find_high_confidence_cells(ad, 8)
+    assert ad.n_obs == hc.sum()
+    Z = ad.X.copy()
+    labels = np.asarray(ad.obs['cluster'])
+    find_relevant_genes(ad, 20, 1, 0)
+    rel_ref = stages.gene_relevance(Z, labels, 0)
+    mask = stages.relevant_mask(rel_ref, 20)
+    assert np.array_equal(np.asarray(ad.var_names), names[mask])
+    assert np.array_equal(ad.var['relevance'].to_numpy(), rel_ref[mask])
+    compute_gene_redundancy(ad, 1, 0)
+    R = ad.varp['redundancy']
+    E = ad.varm['X_pca']
+    rs = np.random.RandomState(0)
+    pairs = np.sort(np.stack([rs.randint(0, len(E), 80), rs.randint(0, len(E), 80)], 1), 1)
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    assert np.array_equal(R[pairs[:, 0], pairs[:, 1]], stages.gene_redundancy(E, 0, pairs))
+    assert np.array_equal(R, R.T)
+    compute_gene_complementarity(ad, 1, 0)
+    edges = ad.uns['mst_edges']
+    assert edges.shape[1] == 2 and len(edges) <= ad.n_vars - 1
+    sample = edges[:: max(1, len(edges) // 12)]
+    ref_c = stages.gene_complementarity(ad.X, labels, sample, 0)
+    assert np.array_equal(ad.uns['mst_edges_complm'][:: max(1, len(edges) // 12)], ref_c)

@@ -1,0 +1,113 @@
+"""Host-side logic of the drop-in boundary, CPU only: argument validation with the reference's error types
+(scGeneClust/_validation.py), fast/ps selection (tl/selection.py) against the golden vectors, MST helper."""
+import os
+
+import numpy as np
+import pytest
+
+from scgeneclust_b200 import AnnDataLite, scGeneClust
+from scgeneclust_b200.tl.selection import compute_deviance, select_from_clusters
+from scgeneclust_b200.tl.information import redundancy_mst
+
+
+def _adata(n=6, g=5):
+    return AnnDataLite(np.arange(n * g, dtype=np.float32).reshape(n, g))
+
+
+@pytest.mark.parametrize("kwargs,exc", [
+    (dict(verbosity=3), ValueError), (dict(version='slow'), ValueError), (dict(modality='xx'), ValueError),
+    (dict(random_state=0.5), TypeError), (dict(max_workers=1.5), TypeError), (dict(max_workers=0), ValueError),
+    (dict(max_workers=10 ** 6), ValueError), (dict(return_info=1), TypeError), (dict(subset=1), TypeError),
+    (dict(post_hoc_filtering=1), TypeError), (dict(version='fast', n_var_clusters=None), TypeError),
+    (dict(version='fast', n_var_clusters=1), ValueError),
+    (dict(version='fast', n_var_clusters=5, modality='st'), ValueError),
+    (dict(version='ps', n_var_clusters=5), TypeError), (dict(version='ps', n_obs_clusters=None), TypeError),
+    (dict(version='ps', n_obs_clusters=1), ValueError),
+    (dict(version='ps', n_obs_clusters=3, n_components=1), ValueError),
+    (dict(version='ps', n_obs_clusters=3, relevant_gene_pct=100), ValueError),
+    (dict(version='ps', n_obs_clusters=3, relevant_gene_pct=2.5), TypeError),
+    (dict(version='ps', n_obs_clusters=3, shape='circle'), ValueError),
+    (dict(version='ps', n_obs_clusters=3, modality='st'), RuntimeWarning),
+    (dict(version='ps', n_obs_clusters=3, modality='st', image=[1]), TypeError),
+])
+def test_argument_errors_match_reference(kwargs, exc):
+    kw = dict(version='fast', n_var_clusters=3)
+    if kwargs.get('version') == 'ps':
+        kw = {}
+    kw.update(kwargs)
+    with pytest.raises(exc):
+        scGeneClust(_adata(), **kw)
+
+
+def test_non_anndata_and_raw_rejected():
+    with pytest.raises(TypeError):
+        scGeneClust(np.zeros((3, 3)), n_var_clusters=2)
+    ad = _adata()
+    ad.raw = object()
+    with pytest.raises(ValueError):
+        scGeneClust(ad, n_var_clusters=2)
+
+
+def test_fast_selection_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fast_cluster_select_small.npz"), allow_pickle=False)
+    ad = AnnDataLite(g["Zres"].copy(), var_names=g["var_names"].astype(object))
+    ad.var['cluster'] = g["labels"]
+    ad.var['closeness'] = g["closeness"]
+    sel = select_from_clusters(ad, 'fast', True, int(g["seed"]))
+    assert np.array_equal(sel.astype(str), g["selected_posthoc"])
+    sel = select_from_clusters(ad, 'fast', False, int(g["seed"]))
+    assert np.array_equal(sel.astype(str), g["selected_plain"])
+    assert np.array_equal(compute_deviance(g["Zres"][:, :8]), g["deviance_first8"], equal_nan=True)
+
+
+def test_fast_selection_tie_rule_first_occurrence():
+    ad = AnnDataLite(np.zeros((2, 6), np.float32), var_names=np.array(list("abcdef"), dtype=object))
+    ad.var['cluster'] = np.array([1, 0, 1, 0, 1, 2], np.int32)
+    ad.var['closeness'] = np.array([1.0, 0.5, 1.0, 0.5, 0.0, 1.0], np.float32)
+    sel = select_from_clusters(ad, 'fast', False, 0)
+    # cluster 0: max first 'b', min first 'b'; cluster 1: max first 'a', min 'e'; cluster 2 singleton dropped
+    assert list(sel) == ['b', 'a', 'b', 'e']
+
+
+def test_ps_selection_rules():
+    names = np.array([f"g{i}" for i in range(8)], dtype=object)
+    ad = AnnDataLite(np.zeros((2, 8), np.float32), var_names=names)
+    ad.var['cluster'] = np.array([0, 0, 0, 1, 1, 1, -1, -1])
+    ad.var['relevance'] = np.array([.1, .9, .9, .3, .2, .1, .5, .6])
+    ad.var['outlier_score'] = np.array([0., .2, .4, 0., .6, .0, .39, .41])
+    sel = select_from_clusters(ad, 'ps', True, 0)   # dense positive scores: .2 .4 .6 -> median .4
+    assert list(sel) == ['g1', 'g3', 'g7']
+    sel = select_from_clusters(ad, 'ps', False, 0)
+    assert list(sel) == ['g1', 'g3']
+
+
+def test_redundancy_mst_is_max_spanning_forest():
+    rs = np.random.RandomState(0)
+    N = 30
+    R = np.triu(rs.rand(N, N), 1)
+    R[R < 0.4] = 0.0              # the reference's graph has no edge where MI == 0
+    R[:, 7] = 0.0; R[7, :] = 0.0  # isolated vertex -> spanning forest
+    R = R + R.T
+    edges = redundancy_mst(R)
+    assert edges.shape == (N - 2, 2) and (edges[:, 0] < edges[:, 1]).all()
+    assert 7 not in edges
+    # total weight equals Kruskal on sorted edges (independent check)
+    iu = np.triu_indices(N, 1)
+    order = np.argsort(-R[iu], kind="stable")
+    parent = list(range(N))
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+    tot = 0.0
+    for e in order:
+        i, j, w = iu[0][e], iu[1][e], R[iu][e]
+        if w == 0:
+            break
+        ri, rj = find(i), find(j)
+        if ri != rj:
+            parent[ri] = rj
+            tot += w
+    assert np.isclose(R[edges[:, 0], edges[:, 1]].sum(), tot, rtol=0, atol=1e-12)
+    assert list(map(tuple, edges)) == sorted(map(tuple, edges))
