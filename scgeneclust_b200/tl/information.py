@@ -74,7 +74,8 @@ def gene_relevance(Z: torch.Tensor, labels, random_state: int = 0, return_counts
     d_label_k = torch.from_numpy(label_k).to(dev)
     m_all = torch.empty((n, G), dtype=torch.int32, device=dev)
     mi = torch.empty(G, dtype=torch.float64, device=dev)
-    L.mi_cd(ptr(XR), n, G, n, ptr(d_label), ptr(d_label_k), len(uniq), float(const_term), ptr(_psi_table(n, dev)),
+    psi = _psi_table(n, dev)
+    L.mi_cd(ptr(XR), n, G, n, ptr(d_label), ptr(d_label_k), len(uniq), float(const_term), ptr(psi),
             ptr(m_all), ptr(mi), stream)
     if return_counts:
         return mi, m_all, keep
@@ -118,8 +119,9 @@ def prepare_pair_roles(E: torch.Tensor, random_state: int = 0):
     seg_off = torch.tensor([0, n], dtype=torch.int32, device=dev)
     XR = torch.empty((N, n), dtype=torch.float64, device=dev)
     YR = torch.empty((N, n), dtype=torch.float64, device=dev)
-    L.mi_prepare(ptr(Et), Et.stride(0), ptr(order), ptr(seg_off), 1, N, n, ptr(torch.from_numpy(xi1).to(dev)),
-                 ptr(torch.from_numpy(xi2).to(dev)), ptr(XR), ptr(YR), stream)
+    d_xi1, d_xi2 = torch.from_numpy(xi1).to(dev), torch.from_numpy(xi2).to(dev)   # keep alive across the launch
+    L.mi_prepare(ptr(Et), Et.stride(0), ptr(order), ptr(seg_off), 1, N, n, ptr(d_xi1), ptr(d_xi2), ptr(XR), ptr(YR),
+                 stream)
     return XR, YR
 
 
@@ -139,8 +141,8 @@ def gene_redundancy(E: torch.Tensor, random_state: int = 0, p_begin: int = 0, p_
     D = torch.zeros((N, N), dtype=torch.float64, device=dev) if dense else None
     nx = torch.empty((p_end - p_begin, n), dtype=torch.uint8, device=dev) if return_counts else None
     ny = torch.empty_like(nx) if return_counts else None
-    L.mi_cc_pairs(ptr(XR), ptr(YR), N, n, n, ptr(_psi_table(n, dev)), p_begin, p_end, ptr(cond), ptr(D), ptr(nx),
-                  ptr(ny), stream)
+    psi = _psi_table(n, dev)
+    L.mi_cc_pairs(ptr(XR), ptr(YR), N, n, n, ptr(psi), p_begin, p_end, ptr(cond), ptr(D), ptr(nx), ptr(ny), stream)
     if return_counts:
         return cond, D, nx, ny
     return cond, D
@@ -218,8 +220,11 @@ def gene_complementarity(Z: torch.Tensor, clusters, edges: np.ndarray, random_st
     Gs = len(genes)
     XR = torch.empty((Gs, n), dtype=torch.float64, device=dev)
     YR = torch.empty((Gs, n), dtype=torch.float64, device=dev)
-    L.mi_prepare(ptr(Zs), Zs.stride(0), ptr(torch.from_numpy(order).to(dev)), ptr(torch.from_numpy(seg_off).to(dev)),
-                 len(uniq), Gs, n, ptr(torch.from_numpy(xi1).to(dev)), ptr(torch.from_numpy(xi2).to(dev)), ptr(XR),
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    # every device argument is bound to a name: a temporary would be freed (and its block reused by the next
+    # upload) before the kernel runs
+    d_order, d_seg, d_xi1, d_xi2 = t(order), t(seg_off), t(xi1), t(xi2)
+    L.mi_prepare(ptr(Zs), Zs.stride(0), ptr(d_order), ptr(d_seg), len(uniq), Gs, n, ptr(d_xi1), ptr(d_xi2), ptr(XR),
                  ptr(YR), stream)
     n_edges, n_c = len(edges), len(uniq)
     e_i = np.repeat(pos[edges[:, 0]], n_c)
@@ -230,13 +235,13 @@ def gene_complementarity(Z: torch.Tensor, clusters, edges: np.ndarray, random_st
     length = cnt[seg].astype(np.int32)
     out_off = np.concatenate([[0], np.cumsum(length[:-1], dtype=np.int64)]).astype(np.int64)
     total = int(length.sum(dtype=np.int64))
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     nx = torch.empty(total, dtype=torch.int32, device=dev)
     ny = torch.empty(total, dtype=torch.int32, device=dev)
     mi = torch.empty(n_edges * n_c, dtype=torch.float64, device=dev)
-    L.mi_cc_problems(ptr(XR), ptr(YR), ptr(t(x_off.astype(np.int64))), ptr(t(y_off.astype(np.int64))), ptr(t(length)),
-                     ptr(t(out_off)), n_edges * n_c, ptr(_psi_table(int(cnt.max()), dev)), ptr(nx), ptr(ny), ptr(mi),
-                     stream)
+    d_xoff, d_yoff, d_len, d_ooff = t(x_off.astype(np.int64)), t(y_off.astype(np.int64)), t(length), t(out_off)
+    psi = _psi_table(int(cnt.max()), dev)
+    L.mi_cc_problems(ptr(XR), ptr(YR), ptr(d_xoff), ptr(d_yoff), ptr(d_len), ptr(d_ooff), n_edges * n_c, ptr(psi),
+                     ptr(nx), ptr(ny), ptr(mi), stream)
     mi_h = mi.cpu().numpy().reshape(n_edges, n_c)
     cmi = np.zeros(n_edges)
     for c in range(n_c):                                        # the reference's accumulation order (np.unique order)
