@@ -45,6 +45,9 @@ enum ProfSlot { kProfRsvdPass = 0, kProfMiPairs = 1, kProfSlots = 2 };
 void prof_begin(int slot, cudaStream_t st);
 void prof_end(int slot, cudaStream_t st);
 
+// scratch need of the SIMT cross-check pass (embed_kernels.cu); gc_rsvd_scratch_bytes covers both kernels
+int64_t simt_scratch_bytes(int64_t C, int64_t G);
+
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 

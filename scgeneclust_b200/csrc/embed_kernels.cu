@@ -544,12 +544,14 @@ extern "C" int gc_residual_sums(const uint16_t *counts, int64_t C, int64_t G, in
     return 0;
 }
 
-extern "C" int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G) {
+namespace gc {
+int64_t simt_scratch_bytes(int64_t C, int64_t G) {
     // worst case over both directions
     const int s0 = choose_split(ceil_div<int64_t>(C, kTileM), G), s1 = choose_split(ceil_div<int64_t>(G, kTileM), C);
     const int64_t b0 = (int64_t)s0 * C * kQ * 4, b1 = (int64_t)s1 * G * kQ * 4;
     return (b0 > b1 ? b0 : b1) + 256;
 }
+}  // namespace gc
 
 extern "C" int gc_rsvd_apply_simt(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q,
                                   void *partials, void *stream) {
