@@ -36,11 +36,13 @@ class AnnDataLite:
         self._X = X
         n_obs, n_vars = X.shape
         if obs is None:
-            names = obs_names if obs_names is not None else [f"cell_{i}" for i in range(n_obs)]
-            obs = pd.DataFrame(index=pd.Index(np.asarray(names, dtype=object)))
+            # default names are '0', '1', ... like anndata; they are materialised on first use of `obs_names` /
+            # `var_names` (building 10^5..10^6 strings up front would cost more than the whole device pipeline)
+            index = pd.Index(np.asarray(obs_names, dtype=object)) if obs_names is not None else pd.RangeIndex(n_obs)
+            obs = pd.DataFrame(index=index)
         if var is None:
-            names = var_names if var_names is not None else [f"gene_{i}" for i in range(n_vars)]
-            var = pd.DataFrame(index=pd.Index(np.asarray(names, dtype=object)))
+            index = pd.Index(np.asarray(var_names, dtype=object)) if var_names is not None else pd.RangeIndex(n_vars)
+            var = pd.DataFrame(index=index)
         if len(obs) != n_obs or len(var) != n_vars:
             raise ValueError("obs/var length does not match X")
         self.obs, self.var = obs, var
@@ -70,13 +72,19 @@ class AnnDataLite:
     def shape(self):
         return self._X.shape
 
+    @staticmethod
+    def _named(frame: pd.DataFrame) -> pd.Index:
+        if isinstance(frame.index, pd.RangeIndex):
+            frame.index = pd.Index(np.arange(len(frame)).astype(str).astype(object))
+        return frame.index
+
     @property
     def obs_names(self) -> pd.Index:
-        return self.obs.index
+        return self._named(self.obs)
 
     @property
     def var_names(self) -> pd.Index:
-        return self.var.index
+        return self._named(self.var)
 
     # -- copy / subset --------------------------------------------------------------------------------------
     def copy(self) -> "AnnDataLite":
@@ -100,14 +108,14 @@ class AnnDataLite:
         return pos
 
     def _inplace_subset_var(self, index) -> None:
-        pos = self._resolve(index, self.var.index)
+        pos = self._resolve(index, self.var_names)
         self._X = self._X[:, pos]
         self.var = self.var.iloc[pos].copy()
         self.varm = {k: np.asarray(v)[pos] for k, v in self.varm.items()}
         self.varp = {k: np.asarray(v)[np.ix_(pos, pos)] for k, v in self.varp.items()}
 
     def _inplace_subset_obs(self, index) -> None:
-        pos = self._resolve(index, self.obs.index)
+        pos = self._resolve(index, self.obs_names)
         self._X = self._X[pos, :]
         self.obs = self.obs.iloc[pos].copy()
         self.obsm = {k: np.asarray(v)[pos] for k, v in self.obsm.items()}

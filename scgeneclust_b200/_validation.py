@@ -81,7 +81,8 @@ def check_gene_clustering(img, version, n_gene_clusters, n_obs_clusters, n_compo
 
 
 def check_all_genes_selected(adata, selected_genes: np.ndarray):
-    is_selected = np.isin(adata.var_names, selected_genes)
+    # hash lookup instead of the reference's np.isin on object arrays (sort-based, ~70 ms for 20 000 names)
+    is_selected = adata.var_names.isin(selected_genes)
     if (n_selected_genes := is_selected.sum()) != selected_genes.shape[0]:
         msg = f"Found only {n_selected_genes} selected genes in `adata.var_names`, not {selected_genes.shape[0]}."
         raise RuntimeError(msg)

@@ -35,6 +35,21 @@ def _residual_columns(adata, mask: np.ndarray) -> np.ndarray:
     return np.asarray(adata.X)[:, mask]
 
 
+def _isolation_forest_outliers(values: np.ndarray, random_state: int) -> np.ndarray:
+    """`IsolationForest(random_state=...).fit_predict(values.reshape(-1, 1)) == -1` (scGeneClust/tl/selection.py:51).
+
+    With one or two samples the forest's answer does not depend on its random draws, so it is written down instead
+    of fitting 100 trees (~0.1 s of Python overhead): max_samples_ = n, so every tree holds all samples; for n = 1
+    the normaliser c(1) = 0 makes every score exactly -0.5, for n = 2 every tree isolates both samples at depth 1
+    (or keeps two equal values in one leaf, path length c(2) = 1) and every score is -2^(-1) = -0.5 as well.
+    `offset_` is -0.5 (contamination='auto'), the decision function is 0 and `predict` flags only values < 0:
+    no outlier.  (sklearn 1.9.0 ensemble/_iforest.py:297-380, :529-640.)  Non-finite input other than NaN makes
+    sklearn raise, so that case - and every n >= 3 - still goes through sklearn itself."""
+    if values.shape[0] <= 2 and not np.isinf(values).any():
+        return np.zeros(values.shape[0], dtype=bool)
+    return IsolationForest(random_state=random_state).fit_predict(values.reshape(-1, 1)) == -1
+
+
 def _first_extreme_per_cluster(cluster: np.ndarray, value: np.ndarray, largest: bool) -> np.ndarray:
     """Positions of the first maximum (or minimum) of `value` inside every cluster, ascending cluster id - what
     `groupby('cluster')[col].nlargest(1)` / `.nsmallest(1)` (keep='first') pick."""
@@ -59,7 +74,7 @@ def select_from_clusters(adata, version: Literal['fast', 'ps'], post_hoc_filteri
         if post_hoc_filtering and (n_single := int(is_single.sum())) > 0:
             single_genes = var_names[is_single]
             deviances = compute_deviance(_residual_columns(adata, is_single))
-            is_outlier = IsolationForest(random_state=random_state).fit_predict(deviances.reshape(-1, 1)) == -1
+            is_outlier = _isolation_forest_outliers(deviances, random_state)
             logger.opt(colors=True).debug(
                 f"Found <yellow>{is_outlier.sum()}</yellow> outlier(s) in <yellow>{n_single}</yellow> single gene cluster(s).")
             outlier_genes = single_genes[is_outlier]
