@@ -13,10 +13,19 @@
 // (measured: tf32 2e-3, bf16 O(1); hi+lo 8e-5).  The Q panel is pre-split once per pass (tiny, L2 resident).
 //
 // CTA = one 128-row output tile x one k-slab (split-K; slabs are reduced in a fixed order by a second kernel, so
-// results are deterministic).  288 threads: warps 0-7 producers (then epilogue), warp 8 MMA issuer + TMEM owner.
-// 2 stages x 48 KB shared memory per CTA, two CTAs per SM so one CTA's prologue/epilogue hides under the other's
-// main loop.  Bound: HBM (algorithmic 2 B/entry); the producer ALU work (~13 instr/entry) is the practical limiter.
+// results are deterministic), one CTA per SM, 608 threads:
+//   warps 0-15  producers (then epilogue): raw count tile (shared memory) -> residual math -> bf16 hi/lo UMMA tile
+//   warp 16     MMA issuer + TMEM owner
+//   warp 17     bulk-copy issuer for the panel tiles (Qh/Ql, stored PRE-SWIZZLED per 64-row tile by the prep kernel, so
+//               one 8 KB cp.async.bulk lands a tile in the UMMA SWIZZLE_128B layout)
+//   warp 18     TMA issuer for the raw count tiles (2-D tensor map over the uint16 matrix, zero fill out of bounds)
+//               and the 64 per-stage constants (s_g/T or r_c)
+// Two shared-memory rings: 5 raw stages (16 KB counts + 256 B constants; 80 KB of HBM reads in flight per SM with no
+// registers or address arithmetic spent on them) and 3 UMMA stages of 48 KB (A hi, A lo, B hi, B lo).
+// Bound: HBM (algorithmic 2 B/entry); the producer ALU work (12 lane-instructions per entry) is the practical limiter.
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <cudaTypedefs.h>
 
 #include "common.cuh"
 
@@ -25,22 +34,35 @@ namespace gc {
 constexpr int TC_TM = 128;           // output rows per CTA (UMMA M)
 constexpr int TC_TN = 64;            // panel width (UMMA N)
 constexpr int TC_TK = 64;            // k per stage (one 128-byte swizzle row of bf16)
-constexpr int TC_STAGES = 2;
-constexpr int TC_PRODUCERS = 256;    // warps 0..7
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_STAGES = 3;         // UMMA operand stages
+constexpr int TC_RAW_STAGES = 5;     // raw count stages
+constexpr int TC_PRODUCER_WARPS = 16;
+constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 96;
 constexpr int TC_A_BYTES = TC_TM * TC_TK * 2;      // 16 KB per half (hi or lo)
 constexpr int TC_B_BYTES = TC_TN * TC_TK * 2;      // 8 KB per half
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int TC_RAW_TILE_BYTES = TC_TM * TC_TK * 2;              // 16 KB of uint16 counts
+constexpr int TC_RAW_BYTES = TC_RAW_TILE_BYTES + TC_TK * 4;       // + 64 float constants
+constexpr int TC_BAR_BYTES = 256;
+// TMEM: two accumulator sets (k-slice parity) x {D1: 128 columns = [A_hi Q_hi | A_hi Q_lo], D2: 64 columns = A_lo Q_hi}.
+// Back-to-back MMAs into ONE accumulator serialise on its read-modify-write (~120 cycles each at N = 64, measured);
+// with four independent accumulators and the hi.hi / hi.lo products fused into one N = 128 MMA they pipeline.
+constexpr int TC_TMEM_SET = 192, TC_TMEM_COLS = 512;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_RAW_STAGES * TC_RAW_BYTES + 1024 /*align*/ + TC_BAR_BYTES;
 
 struct TcArgs {
     const uint16_t *counts; int64_t C, G, ld;
-    const float *row_sum_f, *col_sum_f; float inv_total, inv_theta, clip;
-    const float *row_shift, *col_shift;
-    const __nv_bfloat16 *Qh, *Ql;        // pre-split panel, [n_k][64] each
+    const float *rpad;                   // [ceil128(C)]  r_c  (1.0 beyond C)
+    const float *tpad;                   // [ceil128(ld)] s_g / T (1.0 beyond G)
+    const float *tperm;                  // tpad with every 64-block permuted for conflict-free shared-memory reads:
+                                         // gene 8a + 4h + j of a block sits at h*32 + a*4 + j
+    float inv_theta, clip;
+    uint32_t magic;                      // 0x4B000000 (2^23) as a run-time value: keeps it in a register so that PRMT
+                                         // takes its selector as the immediate (ptxas otherwise re-materialises it)
+    const __nv_bfloat16 *Qh, *Ql;        // pre-split panel, [ceil64(n_k)][64] each, zero rows beyond n_k
     float *partials;                     // [n_split][n_out][64]
     int64_t n_out, n_k; int n_split; int64_t k_per_split;   // multiple of TC_TK
-    int *error_flag;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -51,6 +73,29 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 2-D tiled tensor copy global -> shared (TMA), coordinates {c0 = innermost (column), c1 = row}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -65,6 +110,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 24)) __trap();
+}
+// Same, for waits that are expected to last: back off between polls so the spinning warp does not take issue slots
+// from the warps doing the residual math on the same scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        __nanosleep(64);
+        if (spin > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -87,9 +141,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same, with the 64-bit shared-memory descriptors given as (lo, hi) words - the issuer keeps the constant hi words and
+// only adds byte offsets (>> 4) to the lo words - and the accumulate flag as a compile-time constant.
+// MUST be executed by a whole converged warp with warp-uniform operands: one elected lane issues.  (Issued from a
+// divergent `if (lane == 0)` region instead, ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY loop and feeds its uniform
+// registers through R2UR chains - measured 150 cycles per MMA on the issuing thread against 48 (N = 64) / 64 (N = 128)
+// for the tensor core itself, scripts/microbench/umma_rate.cu.)
+template <bool ACCUM>
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACCUM ? 1 : 0) : "memory");
+}
+// whole-warp variant of umma_commit: one elected lane commits
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -112,9 +200,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b_format BF16 (1)
 // [7,10)/[10,13), a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc(int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t umma_idesc(int a_mn_major, int b_mn_major, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(TC_TN >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
 }
 
 // 16-byte chunk `chunk` (0..7) of 128-byte row `row` inside a 1024-byte-aligned SWIZZLE_128B region
@@ -122,26 +210,44 @@ __device__ __forceinline__ uint32_t swz128(uint32_t row, uint32_t chunk) {
     return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
 }
 
-// residual of one count (low 16 bits of x16), before the centring shifts
-__device__ __forceinline__ float tc_resid(uint32_t x16, float r, float t, float inv_theta, float clip) {
-    const float xf = __uint_as_float(0x4B000000u | x16) - 8388608.0f;   // exact uint16 -> float without I2F
-    const float mu = r * t;
-    const float var = mu * fmaf(mu, inv_theta, 1.0f);
-    const float rs = rsqrtf(var);
-    const float z = fmaf(xf, rs, -mu * rs);
-    return fminf(fmaxf(z, -clip), clip);
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));     // one MUFU.RSQ
+    return y;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// split 8 floats into packed bf16 hi (truncation) and bf16 lo (rounded remainder) chunks
-__device__ __forceinline__ void split8(const float (&z)[8], uint4 &hi, uint4 &lo) {
+// Eight residuals of one 16-byte chunk of counts (x_e = uint16 e of `raw`), row constant r, column constants t[e]:
+//   mu = r t ; z = min((x - mu) * rsqrt(mu (1 + mu/theta)), clip)            (12 lane-instructions per entry)
+// The lower clip is dead code when clip >= sqrt(theta): z >= -sqrt(theta mu / (theta + mu)) > -sqrt(theta).
+// Output: packed bf16 hi (truncation) and bf16 lo (rounded remainder) chunks.
+template <bool LO_CLIP, bool ROW_R>
+__device__ __forceinline__ void resid8(const uint4 &raw, const float (&cr)[8], float fixed, float inv_theta, float clip,
+                                       uint32_t magic, uint4 &hi, uint4 &lo) {
+    // ROW_R: `fixed` is the row constant r and cr[] the per-column t;  else `fixed`... (same product either way)
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
     uint32_t h[4], l[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        const uint32_t b0 = __float_as_uint(z[2 * p]), b1 = __float_as_uint(z[2 * p + 1]);
-        h[p] = __byte_perm(b0, b1, 0x7632);                         // {hi16(b0), hi16(b1)}
-        const float l0 = z[2 * p] - __uint_as_float(b0 & 0xffff0000u);
-        const float l1 = z[2 * p + 1] - __uint_as_float(b1 & 0xffff0000u);
-        const __nv_bfloat162 lp = __floats2bfloat162_rn(l0, l1);     // .x = l0 (low half)
+        float z[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            // exact uint16 -> float: splice the 16 bits under the 2^23 exponent, subtract 2^23
+            const float xf = __uint_as_float(__byte_perm(w[p], magic, e == 0 ? 0x7410 : 0x7432)) - 8388608.0f;
+            const float mu = fixed * cr[2 * p + e];
+            const float var = mu * fmaf(mu, inv_theta, 1.0f);
+            float v = (xf - mu) * rsqrt_approx(var);
+            v = fminf(v, clip);
+            if (LO_CLIP) v = fmaxf(v, -clip);
+            z[e] = v;
+        }
+        const uint32_t b0 = __float_as_uint(z[0]), b1 = __float_as_uint(z[1]);
+        h[p] = __byte_perm(b0, b1, 0x7632);                                  // {hi16(z0), hi16(z1)}
+        const float l0 = z[0] - __uint_as_float(b0 & 0xffff0000u);
+        const float l1 = z[1] - __uint_as_float(b1 & 0xffff0000u);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(l0, l1);             // .x = l0 (low half)
         l[p] = *reinterpret_cast<const uint32_t *>(&lp);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
@@ -149,36 +255,89 @@ __device__ __forceinline__ void split8(const float (&z)[8], uint4 &hi, uint4 &lo
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// panel pre-split: Q fp32 [n_k][64] -> Qh, Ql bf16 (round-to-nearest hi, rounded remainder lo)
+// per-pass preparation (one launch): the input panel Q fp32 [n_k][64] -> Qh, Ql bf16 [ceil64(n_k)][64], stored as
+// pre-swizzled 64-row tiles (zero rows
+// beyond n_k, so out-of-range k never contributes), block-partial column sums of Q and of k_shift[k] * Q[k,:]
+// (for the rank-1 centring correction applied by the reduce kernel), and the padded constant vectors rpad / tpad.
+// Block b owns PREP_ROWS consecutive rows; thread = (row lane 0..15, float4 column group 0..15).
 // ---------------------------------------------------------------------------------------------------------
+constexpr int PREP_ROWS = 128;
 __global__ void __launch_bounds__(256)
-split_panel_kernel(const float *__restrict__ Q, int64_t n4, __nv_bfloat16 *__restrict__ Qh,
-                   __nv_bfloat16 *__restrict__ Ql) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const float4 q = reinterpret_cast<const float4 *>(Q)[i];
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(q.x, q.y), h1 = __floats2bfloat162_rn(q.z, q.w);
-    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-    const __nv_bfloat162 l0 = __floats2bfloat162_rn(q.x - f0.x, q.y - f0.y);
-    const __nv_bfloat162 l1 = __floats2bfloat162_rn(q.z - f1.x, q.w - f1.y);
-    reinterpret_cast<__nv_bfloat162 *>(Qh)[2 * i] = h0;
-    reinterpret_cast<__nv_bfloat162 *>(Qh)[2 * i + 1] = h1;
-    reinterpret_cast<__nv_bfloat162 *>(Ql)[2 * i] = l0;
-    reinterpret_cast<__nv_bfloat162 *>(Ql)[2 * i + 1] = l1;
+tc_prep_kernel(const float *__restrict__ Q, int64_t n_k, int64_t n_k_pad, const float *__restrict__ k_shift,
+               __nv_bfloat16 *__restrict__ Qh, __nv_bfloat16 *__restrict__ Ql, double *__restrict__ colsum_part,
+               const float *__restrict__ row_sum_f, int64_t C, int64_t C_pad, const float *__restrict__ col_sum_f,
+               int64_t G, int64_t G_pad, float inv_total, float *__restrict__ rpad, float *__restrict__ tpad,
+               float *__restrict__ tperm) {
+    __shared__ double red[16][128];
+    const int rl = threadIdx.x >> 4, cg = threadIdx.x & 15;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const int64_t r_base = (int64_t)blockIdx.x * PREP_ROWS;
+#pragma unroll
+    for (int i = 0; i < PREP_ROWS / 16; ++i) {
+        const int64_t r = r_base + rl + 16 * i;
+        if (r >= n_k_pad) break;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n_k) q = reinterpret_cast<const float4 *>(Q)[r * 16 + cg];
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(q.x, q.y), h1 = __floats2bfloat162_rn(q.z, q.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(q.x - f0.x, q.y - f0.y);
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(q.z - f1.x, q.w - f1.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t *>(&h0); hv.y = *reinterpret_cast<const uint32_t *>(&h1);
+        lv.x = *reinterpret_cast<const uint32_t *>(&l0); lv.y = *reinterpret_cast<const uint32_t *>(&l1);
+        // pre-swizzled 64-row tiles: 16-byte chunk c of row rr sits where SWIZZLE_128B wants it in shared memory
+        const int64_t off = (r >> 6) * 8192 + swz128((uint32_t)(r & 63), (uint32_t)(cg >> 1)) + (cg & 1) * 8;
+        *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(Qh) + off) = hv;
+        *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(Ql) + off) = lv;
+        if (r < n_k) {
+            const double sh = k_shift ? (double)k_shift[r] : 0.0;
+            s1[0] += q.x; s1[1] += q.y; s1[2] += q.z; s1[3] += q.w;
+            s2[0] += sh * q.x; s2[1] += sh * q.y; s2[2] += sh * q.z; s2[3] += sh * q.w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[rl][cg * 4 + j] = s1[j]; red[rl][64 + cg * 4 + j] = s2[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s += red[k][threadIdx.x];
+        colsum_part[(int64_t)blockIdx.x * 128 + threadIdx.x] = s;
+    }
+    // padded constants (grid-stride)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C_pad; i += stride)
+        rpad[i] = i < C ? row_sum_f[i] : 1.0f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < G_pad; i += stride) {
+        const float t = i < G ? col_sum_f[i] * inv_total : 1.0f;
+        tpad[i] = t;
+        const int w = (int)(i & 63);                       // 8a + 4h + j  ->  h*32 + a*4 + j
+        tperm[(i & ~(int64_t)63) + ((w >> 2) & 1) * 32 + (w >> 3) * 4 + (w & 3)] = t;
+    }
+}
+
+// colsum[0..63] = sum_k Q[k,:], colsum[64..127] = sum_k k_shift[k] Q[k,:]   (fixed block order => deterministic)
+__global__ void tc_colsum_kernel(const double *__restrict__ part, int n_blocks, float *__restrict__ colsum) {
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * 128 + threadIdx.x];
+    colsum[threadIdx.x] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int TRANS>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-rsvd_apply_tc_kernel(const TcArgs a) {
+template <int TRANS, bool LO_CLIP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rsvd_apply_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-    // barriers: full[s] @ +8s, empty[s] @ +16+8s, accum @ +32 ; tmem address @ +40
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + TC_STAGES * TC_STAGE_BYTES + 40);
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t raw_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t bar_base = raw_base + TC_RAW_STAGES * TC_RAW_BYTES;
+    // barriers (8 B each): full[S] | empty[S] | raw_full[R] | raw_empty[R] | accum ; then the TMEM address slot
+    const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * TC_STAGES, bar_rfull = bar_empty + 8 * TC_STAGES,
+                   bar_rempty = bar_rfull + 8 * TC_RAW_STAGES, bar_accum = bar_rempty + 8 * TC_RAW_STAGES;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (bar_accum + 8 - smem_base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * TC_TM;
@@ -186,217 +345,212 @@ rsvd_apply_tc_kernel(const TcArgs a) {
     const int64_t k_lo = split * a.k_per_split, k_hi = min(a.n_k, k_lo + a.k_per_split);
     const int n_it = (int)ceil_div<int64_t>(max((int64_t)0, k_hi - k_lo), TC_TK);
 
-    if (warp == 8) {
+    if (warp == TC_PRODUCER_WARPS) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) {
-                mbar_init(bar_base + 8 * s, TC_PRODUCERS / 32);   // one arrive per producer warp
-                mbar_init(bar_base + 16 + 8 * s, 1);              // tcgen05.commit
+                mbar_init(bar_full + 8 * s, TC_PRODUCER_WARPS + 1);   // one arrive per producer warp + the panel copier
+                mbar_init(bar_empty + 8 * s, 1);                      // tcgen05.commit
             }
-            mbar_init(bar_base + 32, 1);
+            for (int s = 0; s < TC_RAW_STAGES; ++s) {
+                mbar_init(bar_rfull + 8 * s, 1);                      // the TMA issuer's arrive.expect_tx
+                mbar_init(bar_rempty + 8 * s, TC_PRODUCER_WARPS);     // one arrive per producer warp
+            }
+            mbar_init(bar_accum, 1);
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(smem_u32((const void *)tmem_slot), TC_TN);    // 64 fp32 accumulator columns
+        tmem_alloc(smem_u32((const void *)tmem_slot), TC_TMEM_COLS);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < TC_PRODUCER_WARPS) {
         // =============================== producers ===============================
-        // TRANS 0: A tile = 128 cells x 64 genes, K-major.   chunk col j = tid%8 (8 genes), rows tid/8 + 32 i
-        // TRANS 1: A tile = 128 genes x 64 cells, MN-major.  chunk col jj = tid%16 (8 genes), cells tid/16 + 16 i
-        // B tile  = 64 k x 64 n (hi, lo), MN-major: row = k, chunk = 8 panel columns; thread -> rows tid/8 + 32 i
+        // TRANS 0: A tile = 128 cells x 64 genes, K-major.   chunk col = tid%8 (8 genes), rows tid/8 + 64 i
+        //          raw tile rows are 128 B (64 genes); constants = s_g/T of the stage's 64 genes
+        // TRANS 1: A tile = 128 genes x 64 cells, MN-major.  chunk col = tid%16 (8 genes), cells tid/16 + 32 i
+        //          raw tile rows are 256 B (128 genes); constants = r_c of the stage's 64 cells
+        // No bounds predicates: the TMA zero-fills counts outside the matrix, rpad/tpad are 1 there (finite residuals),
+        // out-of-range k meets zero rows of Qh/Ql and out-of-range output rows are never stored.
         const int a_col = TRANS == 0 ? (tid & 7) : (tid & 15);
         const int a_row0 = TRANS == 0 ? (tid >> 3) : (tid >> 4);
-        constexpr int A_ROW_STEP = TRANS == 0 ? 32 : 16;
-        const int b_chunk = tid & 7, b_row0 = tid >> 3;
+        constexpr int A_ROW_STEP = TRANS == 0 ? 64 : 32;
+        // shared-memory chunk offsets are affine in i (row + 64 i / + 32 i keeps row & 7): base + immediate
+        constexpr uint32_t A_OFF_STEP = TRANS == 0 ? 8192u : 4096u;
+        const uint32_t a_off0 = TRANS == 0 ? swz128(a_row0, a_col)
+                                           : (uint32_t)(a_col >> 3) * 8192u + swz128(a_row0, a_col & 7);
+        constexpr uint32_t RAW_ROW_BYTES = TRANS == 0 ? 128u : 256u;
+        const uint32_t raw_off0 = (uint32_t)a_row0 * RAW_ROW_BYTES + (uint32_t)a_col * 16u;
+        const uint32_t cst_off0 = TC_RAW_TILE_BYTES + (TRANS == 0 ? (uint32_t)a_col * 16u : (uint32_t)a_row0 * 4u);
 
-        // per-thread constants
-        float r_c[4] = {0.f, 0.f, 0.f, 0.f}, sh_c[4] = {0.f, 0.f, 0.f, 0.f};   // TRANS 0: fixed cells
-        float t_g[8], sh_g[8];                                                  // TRANS 1: fixed genes
-        bool g_ok[8];
+        float fix[8];                  // TRANS 0: r of the 2 cells (fix[0..1]); TRANS 1: t of the 8 genes
         if (TRANS == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t c = m0 + a_row0 + A_ROW_STEP * i;
-                if (c < a.C) { r_c[i] = a.row_sum_f[c]; sh_c[i] = a.row_shift ? a.row_shift[c] : 0.f; }
-            }
+            for (int i = 0; i < 2; ++i) fix[i] = __ldg(a.rpad + m0 + a_row0 + A_ROW_STEP * i);   // rpad covers ceil128(C)
         } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int64_t g = m0 + a_col * 8 + e;
-                g_ok[e] = g < a.G;
-                t_g[e] = g_ok[e] ? a.col_sum_f[g] * a.inv_total : 1.f;
-                sh_g[e] = (g_ok[e] && a.col_shift) ? a.col_shift[g] : 0.f;
-            }
+            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.tpad + m0 + a_col * 8));    // tpad covers ceil128(ld)
+            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.tpad + m0 + a_col * 8) + 1);
+            fix[0] = t0.x; fix[1] = t0.y; fix[2] = t0.z; fix[3] = t0.w;
+            fix[4] = t1.x; fix[5] = t1.y; fix[6] = t1.z; fix[7] = t1.w;
         }
 
-        uint4 raw[4], qh[2], ql[2];
-        float4 tgv[2], shv[2];     // TRANS 0: per-stage gene constants of this thread's 8 genes
-        float rcs[4], shs[4];      // TRANS 1: per-stage cell constants of this thread's 4 cells
-        auto load_stage = [&](int it) {
-            const int64_t kk = k_lo + (int64_t)it * TC_TK;
-            if (TRANS == 0) {
-                const int64_t g0 = kk + a_col * 8;
-                const bool gin = g0 < a.ld;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t c = m0 + a_row0 + A_ROW_STEP * i;
-                    raw[i] = (c < a.C && gin) ? __ldg(reinterpret_cast<const uint4 *>(a.counts + c * a.ld + g0))
-                                              : make_uint4(0, 0, 0, 0);
-                }
-                float tt[8], ss[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int64_t g = g0 + e;
-                    const bool ok = g < k_hi;          // k_hi <= G
-                    tt[e] = ok ? __ldg(a.col_sum_f + g) * a.inv_total : 0.f;
-                    ss[e] = (ok && a.col_shift) ? __ldg(a.col_shift + g) : 0.f;
-                }
-                tgv[0] = make_float4(tt[0], tt[1], tt[2], tt[3]); tgv[1] = make_float4(tt[4], tt[5], tt[6], tt[7]);
-                shv[0] = make_float4(ss[0], ss[1], ss[2], ss[3]); shv[1] = make_float4(ss[4], ss[5], ss[6], ss[7]);
-            } else {
-                const int64_t g0 = m0 + a_col * 8;
-                const bool gin = g0 < a.ld;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t c = kk + a_row0 + A_ROW_STEP * i;
-                    const bool ok = c < k_hi;          // k_hi <= C
-                    raw[i] = (ok && gin) ? __ldg(reinterpret_cast<const uint4 *>(a.counts + c * a.ld + g0))
-                                         : make_uint4(0, 0, 0, 0);
-                    rcs[i] = ok ? __ldg(a.row_sum_f + c) : 0.f;
-                    shs[i] = (ok && a.row_shift) ? __ldg(a.row_shift + c) : 0.f;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int64_t kr = kk + b_row0 + 32 * i;
-                if (kr < k_hi) {
-                    qh[i] = __ldg(reinterpret_cast<const uint4 *>(a.Qh + kr * TC_TN + b_chunk * 8));
-                    ql[i] = __ldg(reinterpret_cast<const uint4 *>(a.Ql + kr * TC_TN + b_chunk * 8));
-                } else {
-                    qh[i] = make_uint4(0, 0, 0, 0); ql[i] = make_uint4(0, 0, 0, 0);
-                }
-            }
-        };
-
-        auto store_stage = [&](int it, uint8_t *st) {
-            const int64_t kk = k_lo + (int64_t)it * TC_TK;
-            uint8_t *a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = b_hi + TC_B_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-                float z[8];
-                if (TRANS == 0) {
-                    const float tt[8] = {tgv[0].x, tgv[0].y, tgv[0].z, tgv[0].w, tgv[1].x, tgv[1].y, tgv[1].z, tgv[1].w};
-                    const float ss[8] = {shv[0].x, shv[0].y, shv[0].z, shv[0].w, shv[1].x, shv[1].y, shv[1].z, shv[1].w};
-                    const bool row_ok = (m0 + a_row0 + A_ROW_STEP * i) < a.C;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const uint32_t x16 = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-                        const float v = tc_resid(x16, r_c[i], tt[e], a.inv_theta, a.clip) - sh_c[i] - ss[e];
-                        z[e] = (row_ok && tt[e] > 0.f) ? v : 0.f;     // tt == 0 marks k >= k_hi
-                    }
-                } else {
-                    const bool cell_ok = (kk + a_row0 + A_ROW_STEP * i) < k_hi;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const uint32_t x16 = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-                        const float v = tc_resid(x16, rcs[i], t_g[e], a.inv_theta, a.clip) - shs[i] - sh_g[e];
-                        z[e] = (cell_ok && g_ok[e]) ? v : 0.f;
-                    }
-                }
-                uint4 hi, lo;
-                split8(z, hi, lo);
-                uint32_t off;
-                if (TRANS == 0) off = swz128(a_row0 + A_ROW_STEP * i, a_col);
-                else off = (uint32_t)(a_col >> 3) * 8192u + swz128(a_row0 + A_ROW_STEP * i, a_col & 7);
-                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const uint32_t off = swz128(b_row0 + 32 * i, b_chunk);
-                *reinterpret_cast<uint4 *>(b_hi + off) = qh[i];
-                *reinterpret_cast<uint4 *>(b_lo + off) = ql[i];
-            }
-        };
-
-        if (n_it > 0) load_stage(0);
         for (int it = 0; it < n_it; ++it) {
-            const int s = it % TC_STAGES;
-            const uint32_t ph = (it / TC_STAGES) & 1;
-            mbar_wait(bar_base + 16 + 8 * s, ph ^ 1);         // stage free (passes at once on the first lap)
-            store_stage(it, smem + s * TC_STAGE_BYTES);
-            if (it + 1 < n_it) load_stage(it + 1);            // next global loads fly while the MMA runs
+            const int s = it % TC_STAGES, rs = it % TC_RAW_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1, rph = (it / TC_RAW_STAGES) & 1;
+            const uint32_t rb = raw_base + rs * TC_RAW_BYTES;
+            mbar_wait_backoff(bar_rfull + 8 * rs, rph);       // raw counts + constants have landed
+            uint4 raw[2];
+            float cst[TRANS == 0 ? 8 : 2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) raw[i] = lds128(rb + raw_off0 + A_ROW_STEP * RAW_ROW_BYTES * i);
+            if constexpr (TRANS == 0) {
+                const uint4 c0 = lds128(rb + cst_off0), c1 = lds128(rb + cst_off0 + 128);   // permuted block: conflict-free
+                cst[0] = __uint_as_float(c0.x); cst[1] = __uint_as_float(c0.y); cst[2] = __uint_as_float(c0.z);
+                cst[3] = __uint_as_float(c0.w); cst[4] = __uint_as_float(c1.x); cst[5] = __uint_as_float(c1.y);
+                cst[6] = __uint_as_float(c1.z); cst[7] = __uint_as_float(c1.w);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) cst[i] = lds32f(rb + cst_off0 + A_ROW_STEP * 4 * i);
+            }
+            uint4 hi[2], lo[2];                               // the math first, the wait for a free UMMA stage after it
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if constexpr (TRANS == 0) resid8<LO_CLIP, true>(raw[i], cst, fix[i], a.inv_theta, a.clip, a.magic, hi[i], lo[i]);
+                else resid8<LO_CLIP, false>(raw[i], fix, cst[i], a.inv_theta, a.clip, a.magic, hi[i], lo[i]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);  // this warp is done reading the raw stage
+            mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1);     // UMMA stage free (passes at once on the first lap)
+            const uint32_t st = smem_base + s * TC_STAGE_BYTES + a_off0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                sts128(st + A_OFF_STEP * i, hi[i]);
+                sts128(st + TC_A_BYTES + A_OFF_STEP * i, lo[i]);
+            }
             fence_proxy_async_smem();                         // generic-proxy writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8 * s);
+            if (lane == 0) mbar_arrive(bar_full + 8 * s);
         }
 
         // =============================== epilogue ===============================
-        // warp w reads TMEM lanes 32 (w % 4) .. +31 (= output rows), column half w / 4
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (= output rows), column quarter w / 4
         if (n_it > 0) {
-            mbar_wait(bar_base + 32, 0);
+            mbar_wait(bar_accum, 0);
             tc_fence_after();
         }
-        const int lane_grp = warp & 3, col_half = warp >> 2;
-        uint32_t v[32];
-        if (n_it > 0) {
-            tmem_ld32(tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(col_half * 32), v);
-        } else {
+        const int lane_grp = warp & 3, col_q = warp >> 2;
+        float acc[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0u;
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        if (n_it > 0) {
+            // fixed summation order: set 0 {hi.hi, hi.lo, lo.hi}, then set 1
+            const uint32_t t0 = tmem_d + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(col_q * 16);
+#pragma unroll
+            for (int part = 0; part < 6; ++part) {
+                uint32_t v[16];
+                tmem_ld16(t0 + (part / 3) * TC_TMEM_SET + (part % 3) * 64, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+            }
         }
         const int64_t row = m0 + lane_grp * 32 + lane;
         if (row < a.n_out) {
-            float4 *dst = reinterpret_cast<float4 *>(a.partials + ((int64_t)split * a.n_out + row) * TC_TN + col_half * 32);
+            float4 *dst = reinterpret_cast<float4 *>(a.partials + ((int64_t)split * a.n_out + row) * TC_TN + col_q * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 4; ++j)
+                dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
-    } else {
-        // =============================== MMA issuer (one thread) ===============================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(TRANS == 0 ? 0 : 1, 1);
+    } else if (warp == TC_PRODUCER_WARPS) {
+        // =============================== MMA issuer (whole warp, one elected lane issues) =============
+        {
+            constexpr uint32_t idesc128 = umma_idesc(TRANS == 0 ? 0 : 1, 1, 128), idesc64 = umma_idesc(TRANS == 0 ? 0 : 1, 1, 64);
             // A: K-major (TRANS 0): SBO = 1024 (next 8 rows), K step = 32 B.
             //    MN-major (TRANS 1): LBO = 8192 (next 64 genes), SBO = 1024 (next 8 cells), K step = 2048 B.
-            // B: MN-major: one 64-wide block, SBO = 1024 (next 8 k), K step = 2048 B.
+            // B: MN-major, LBO = 8192 (next 64 panel columns: B_lo sits right behind B_hi, so ONE N = 128 descriptor covers
+            //    [Q_hi | Q_lo]), SBO = 1024 (next 8 k), K step = 2048 B.
+            // The issuing thread is on the critical path of every stage, so the descriptors are built once: per MMA only
+            // the start-address field of the lo word changes (byte offset >> 4, no carry out of its 14 bits because
+            // shared memory is < 256 KB).
             constexpr uint32_t a_lbo = TRANS == 0 ? 16u : 8192u, a_sbo = 1024u, a_kstep = TRANS == 0 ? 32u : 2048u;
             constexpr uint32_t b_lbo = 8192u, b_sbo = 1024u, b_kstep = 2048u;
+            const uint64_t da0 = umma_desc(smem_base, a_lbo, a_sbo), db0 = umma_desc(smem_base + 2 * TC_A_BYTES, b_lbo, b_sbo);
+            const uint32_t a_hiw = (uint32_t)(da0 >> 32), b_hiw = (uint32_t)(db0 >> 32);
+            const uint32_t a_low0 = (uint32_t)da0, b_low0 = (uint32_t)db0;
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % TC_STAGES;
                 const uint32_t ph = (it / TC_STAGES) & 1;
-                mbar_wait(bar_base + 8 * s, ph);
+                mbar_wait(bar_full + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-                const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+                const uint32_t a_st = a_low0 + (uint32_t)s * (TC_STAGE_BYTES >> 4), b_st = b_low0 + (uint32_t)s * (TC_STAGE_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < TC_TK / 16; ++k) {
-                    const uint64_t dah = umma_desc(a_hi + k * a_kstep, a_lbo, a_sbo);
-                    const uint64_t dal = umma_desc(a_lo + k * a_kstep, a_lbo, a_sbo);
-                    const uint64_t dbh = umma_desc(b_hi + k * b_kstep, b_lbo, b_sbo);
-                    const uint64_t dbl = umma_desc(b_lo + k * b_kstep, b_lbo, b_sbo);
-                    umma_bf16(tmem_d, dah, dbh, idesc, (it | k) != 0 ? 1u : 0u);
-                    umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+                    const uint32_t ah = a_st + k * (a_kstep >> 4), al = ah + (TC_A_BYTES >> 4);
+                    const uint32_t bh = b_st + k * (b_kstep >> 4);
+                    const uint32_t d1 = tmem_d + (k & 1) * TC_TMEM_SET, d2 = d1 + 128;
+                    if (k < 2) {       // first use of this accumulator set in the stage: overwrite on the first stage
+                        if (it == 0) {
+                            umma_bf16_w<false>(d1, ah, a_hiw, bh, b_hiw, idesc128);
+                            umma_bf16_w<false>(d2, al, a_hiw, bh, b_hiw, idesc64);
+                        } else {
+                            umma_bf16_w<true>(d1, ah, a_hiw, bh, b_hiw, idesc128);
+                            umma_bf16_w<true>(d2, al, a_hiw, bh, b_hiw, idesc64);
+                        }
+                    } else {
+                        umma_bf16_w<true>(d1, ah, a_hiw, bh, b_hiw, idesc128);
+                        umma_bf16_w<true>(d2, al, a_hiw, bh, b_hiw, idesc64);
+                    }
                 }
-                umma_commit(bar_base + 16 + 8 * s);           // frees the stage when these MMAs have read it
+                umma_commit_elect(bar_empty + 8 * s);         // frees the stage when these MMAs have read it
             }
-            if (n_it > 0) umma_commit(bar_base + 32);         // accumulator complete
+            if (n_it > 0) umma_commit_elect(bar_accum);       // accumulator complete
+        }
+        __syncwarp();
+    } else if (warp == TC_PRODUCER_WARPS + 1) {
+        // =============================== panel-tile copy issuer (one thread) ===============================
+        if (lane == 0) {
+            const char *qh = reinterpret_cast<const char *>(a.Qh) + (k_lo / TC_TK) * TC_B_BYTES;
+            const char *ql = reinterpret_cast<const char *>(a.Ql) + (k_lo / TC_TK) * TC_B_BYTES;
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (it / TC_STAGES) & 1;
+                mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1);
+                const uint32_t b_hi = smem_base + s * TC_STAGE_BYTES + 2 * TC_A_BYTES;
+                mbar_arrive_expect_tx(bar_full + 8 * s, 2 * TC_B_BYTES);
+                bulk_g2s(b_hi, qh + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_full + 8 * s);
+                bulk_g2s(b_hi + TC_B_BYTES, ql + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_full + 8 * s);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== raw count tile TMA issuer (one thread) ===============================
+        if (lane == 0) {
+            const float *cst_src = (TRANS == 0 ? a.tperm : a.rpad) + k_lo;       // 64 floats per stage
+            for (int it = 0; it < n_it; ++it) {
+                const int rs = it % TC_RAW_STAGES;
+                const uint32_t rph = (it / TC_RAW_STAGES) & 1;
+                mbar_wait_backoff(bar_rempty + 8 * rs, rph ^ 1);
+                const uint32_t rb = raw_base + rs * TC_RAW_BYTES;
+                const int32_t kk = (int32_t)(k_lo + (int64_t)it * TC_TK);
+                mbar_arrive_expect_tx(bar_rfull + 8 * rs, TC_RAW_BYTES);
+                if (TRANS == 0) tma_load_2d(rb, &tmap, kk, (int32_t)m0, bar_rfull + 8 * rs);      // {gene, cell}
+                else tma_load_2d(rb, &tmap, (int32_t)m0, kk, bar_rfull + 8 * rs);
+                bulk_g2s(rb + TC_RAW_TILE_BYTES, cst_src + (int64_t)it * TC_TK, TC_TK * 4, bar_rfull + 8 * rs);
+            }
         }
         __syncwarp();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_d, TC_TN);
+    if (warp == TC_PRODUCER_WARPS) tmem_dealloc(tmem_d, TC_TMEM_COLS);
 }
 
+// Y[row, :] = sum_p partials[p][row, :]  -  out_shift[row] * colsum[0..63]  -  colsum[64..127]
+// (fixed summation order => deterministic; the last two terms are the implicit PCA centring, a rank-1 correction)
 __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_t n_elem4, int n_split,
+                                      const float *__restrict__ out_shift, const float *__restrict__ colsum,
                                       float *__restrict__ Y) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_elem4) return;
@@ -405,12 +559,18 @@ __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_
         const float4 v = reinterpret_cast<const float4 *>(partials)[(int64_t)p * n_elem4 + i];
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+    const int cg = (int)(i & 15);
+    const float4 c1 = reinterpret_cast<const float4 *>(colsum)[cg];
+    const float4 c2 = reinterpret_cast<const float4 *>(colsum)[16 + cg];
+    const float sh = out_shift ? out_shift[i >> 4] : 0.f;
+    s.x = s.x - sh * c1.x - c2.x; s.y = s.y - sh * c1.y - c2.y;
+    s.z = s.z - sh * c1.z - c2.z; s.w = s.w - sh * c1.w - c2.w;
     reinterpret_cast<float4 *>(Y)[i] = s;
 }
 
-// split-K heuristic: fill a whole number of waves of (148 SMs x 2 resident CTAs)
+// split-K heuristic: fill a whole number of waves of 148 CTAs (one per SM)
 __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
-    const int64_t slots = (int64_t)kNumSMs * 2;
+    const int64_t slots = (int64_t)kNumSMs;
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 64; ++s) {
@@ -428,16 +588,81 @@ __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
 using namespace gc;
 
 static int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+static int64_t ceil64(int64_t x) { return (x + 63) / 64 * 64; }
+static int64_t ceil128(int64_t x) { return (x + 127) / 128 * 128; }
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }();
+    return fn;
+}
+
+// 2-D tensor map over the uint16 count matrix (C rows x G columns, row pitch ld): box = box_cols x box_rows
+static int make_counts_tmap(CUtensorMap *tm, const uint16_t *counts, int64_t C, int64_t G, int64_t ld, uint32_t box_cols,
+                            uint32_t box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return gc::fail("gc_rsvd_apply", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)C};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(counts), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gc::fail("cuTensorMapEncodeTiled", "failed to encode the count-matrix tensor map");
+    return 0;
+}
+
+struct TcScratch {
+    float *partials; __nv_bfloat16 *Qh, *Ql; double *colsum_part; float *colsum, *rpad, *tpad, *tperm;
+    int n_split; int64_t k_per_split; int prep_blocks; int64_t bytes;
+};
+
+// carve the caller's scratch for one pass direction
+static TcScratch tc_layout(char *base, int64_t C, int64_t ld, int64_t n_out, int64_t n_k) {
+    TcScratch s;
+    s.n_split = tc_choose_split(ceil_div<int64_t>(n_out, TC_TM), n_k);
+    s.k_per_split = ceil_div<int64_t>(ceil_div<int64_t>(n_k, s.n_split), TC_TK) * TC_TK;
+    const int64_t n_k_pad = ceil64(n_k);
+    s.prep_blocks = (int)ceil_div<int64_t>(n_k_pad, PREP_ROWS);
+    char *p = base;
+    s.partials = (float *)p;             p += align256((int64_t)s.n_split * n_out * TC_TN * 4);
+    s.Qh = (__nv_bfloat16 *)p;           p += align256(n_k_pad * TC_TN * 2);
+    s.Ql = (__nv_bfloat16 *)p;           p += align256(n_k_pad * TC_TN * 2);
+    s.colsum_part = (double *)p;         p += align256((int64_t)s.prep_blocks * 128 * 8);
+    s.colsum = (float *)p;               p += 512;
+    s.rpad = (float *)p;                 p += align256(ceil128(C) * 4);
+    s.tpad = (float *)p;                 p += align256(ceil128(ld) * 4);
+    s.tperm = (float *)p;                p += align256(ceil128(ld) * 4);
+    s.bytes = p - base;
+    return s;
+}
 
 extern "C" int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G) {
-    // per direction: split-K partials + the pre-split bf16 panel (hi, lo); worst case over both directions
-    auto need = [](int64_t n_out, int64_t n_k) {
-        const int s = tc_choose_split(ceil_div<int64_t>(n_out, TC_TM), n_k);
-        return align256((int64_t)s * n_out * TC_TN * 4) + 2 * align256(n_k * TC_TN * 2);
-    };
-    const int64_t b0 = need(C, G), b1 = need(G, C);
+    // worst case over both pass directions (ld <= ceil64(G) + 64 covers any padding the caller uses)
+    const int64_t ld = ceil64(G) + 64;
+    const int64_t b0 = tc_layout(nullptr, C, ld, C, G).bytes, b1 = tc_layout(nullptr, C, ld, G, C).bytes;
     const int64_t simt = simt_scratch_bytes(C, G);   // the SIMT cross-check kernel shares the buffer
-    return std::max(std::max(b0, b1), simt) + 512;
+    return std::max(std::max(b0, b1), simt) + 1024;
+}
+
+template <int TRANS, bool LO_CLIP>
+static int tc_launch(const TcArgs &a, const CUtensorMap &tmap, dim3 grid, cudaStream_t st) {
+    static thread_local bool configured = false;
+    if (!configured) {
+        GC_CUDA(cudaFuncSetAttribute(rsvd_apply_tc_kernel<TRANS, LO_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_BYTES));
+        configured = true;
+    }
+    rsvd_apply_tc_kernel<TRANS, LO_CLIP><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, tmap);
+    return 0;
 }
 
 extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *scratch,
@@ -445,45 +670,50 @@ extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float
     GC_REQUIRE(M && Qin && Y && scratch, "null pointer");
     GC_REQUIRE(M->counts != nullptr && M->C >= 1 && M->G >= 1, "empty matrix");
     GC_REQUIRE(M->ld >= M->G && M->ld % 8 == 0 && ((uintptr_t)M->counts & 15) == 0, "counts: ld % 8 == 0, 16-byte aligned");
+    GC_REQUIRE(M->ld <= ceil64(M->G) + 64, "counts: leading dimension padded by more than 127 columns");
     GC_REQUIRE(q >= 1 && q <= TC_TN, "q must be in [1, 64]");
     GC_REQUIRE(trans == 0 || trans == 1, "trans must be 0 or 1");
     GC_REQUIRE(((uintptr_t)Qin & 15) == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)scratch & 255) == 0, "alignment");
+    GC_REQUIRE(M->total > 0.f && M->theta > 0.f, "total and theta must be positive");
     cudaStream_t st = as_stream(stream);
     TcArgs a;
     a.counts = M->counts; a.C = M->C; a.G = M->G; a.ld = M->ld;
-    a.row_sum_f = M->row_sum_f; a.col_sum_f = M->col_sum_f;
-    a.inv_total = 1.0f / M->total; a.inv_theta = 1.0f / M->theta; a.clip = M->clip;
-    a.row_shift = M->row_shift; a.col_shift = M->col_shift;
+    a.inv_theta = 1.0f / M->theta; a.clip = M->clip; a.magic = 0x4B000000u;
     a.n_out = trans == 0 ? M->C : M->G;
     a.n_k = trans == 0 ? M->G : M->C;
+    const TcScratch s = tc_layout((char *)scratch, M->C, M->ld, a.n_out, a.n_k);
+    a.n_split = s.n_split; a.k_per_split = s.k_per_split;
+    a.partials = s.partials; a.Qh = s.Qh; a.Ql = s.Ql; a.rpad = s.rpad; a.tpad = s.tpad; a.tperm = s.tperm;
     const int64_t n_tiles = ceil_div<int64_t>(a.n_out, TC_TM);
-    a.n_split = tc_choose_split(n_tiles, a.n_k);
-    a.k_per_split = ceil_div<int64_t>(ceil_div<int64_t>(a.n_k, a.n_split), TC_TK) * TC_TK;
-    char *p = (char *)scratch;
-    a.partials = (float *)p;                         p += align256((int64_t)a.n_split * a.n_out * TC_TN * 4);
-    __nv_bfloat16 *Qh = (__nv_bfloat16 *)p;          p += align256(a.n_k * TC_TN * 2);
-    __nv_bfloat16 *Ql = (__nv_bfloat16 *)p;
-    a.Qh = Qh; a.Ql = Ql;
-    a.error_flag = nullptr;
+    // centring: M = Z - row_shift[c] - col_shift[g]; the shift indexed by k goes into colsum[64..], the one indexed by
+    // the output row multiplies colsum[0..63]
+    const float *k_shift = trans == 0 ? M->col_shift : M->row_shift;
+    const float *out_shift = trans == 0 ? M->row_shift : M->col_shift;
 
-    const int64_t n4 = a.n_k * TC_TN / 4;
-    split_panel_kernel<<<(unsigned)ceil_div<int64_t>(n4, 256), 256, 0, st>>>(Qin, n4, Qh, Ql);
-    if (int rc = check_launch("split_panel_kernel")) return rc;
+    tc_prep_kernel<<<s.prep_blocks, 256, 0, st>>>(Qin, a.n_k, ceil64(a.n_k), k_shift, s.Qh, s.Ql, s.colsum_part,
+                                                  M->row_sum_f, M->C, ceil128(M->C), M->col_sum_f, M->G, ceil128(M->ld),
+                                                  1.0f / M->total, s.rpad, s.tpad, s.tperm);
+    if (int rc = check_launch("tc_prep_kernel")) return rc;
+    tc_colsum_kernel<<<1, 128, 0, st>>>(s.colsum_part, s.prep_blocks, s.colsum);
+    if (int rc = check_launch("tc_colsum_kernel")) return rc;
 
-    static thread_local bool configured = false;
-    if (!configured) {
-        GC_CUDA(cudaFuncSetAttribute(rsvd_apply_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        GC_CUDA(cudaFuncSetAttribute(rsvd_apply_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        configured = true;
-    }
     GC_REQUIRE(a.n_split <= 65535, "too many k slabs");
+    GC_REQUIRE(M->C < (1ll << 31) && M->ld < (1ll << 31), "matrix dimensions must fit in int32 (TMA coordinates)");
+    CUtensorMap tmap;
+    if (int rc = trans == 0 ? make_counts_tmap(&tmap, M->counts, M->C, M->G, M->ld, TC_TK, TC_TM)
+                            : make_counts_tmap(&tmap, M->counts, M->C, M->G, M->ld, TC_TM, TC_TK))
+        return rc;
     dim3 grid((unsigned)n_tiles, (unsigned)a.n_split);
+    const bool lo_clip = !(M->clip * M->clip >= M->theta);     // z > -sqrt(theta) always: lower clip is dead otherwise
     prof_begin(kProfRsvdPass, st);
-    if (trans == 0) rsvd_apply_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
-    else rsvd_apply_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+    int rc;
+    if (trans == 0) rc = lo_clip ? tc_launch<0, true>(a, tmap, grid, st) : tc_launch<0, false>(a, tmap, grid, st);
+    else rc = lo_clip ? tc_launch<1, true>(a, tmap, grid, st) : tc_launch<1, false>(a, tmap, grid, st);
     prof_end(kProfRsvdPass, st);
-    if (int rc = check_launch("rsvd_apply_tc_kernel")) return rc;
+    if (rc) return rc;
+    if (int rc2 = check_launch("rsvd_apply_tc_kernel")) return rc2;
     const int64_t o4 = a.n_out * TC_TN / 4;
-    rsvd_tc_reduce_kernel<<<(unsigned)ceil_div<int64_t>(o4, 256), 256, 0, st>>>(a.partials, o4, a.n_split, Y);
+    rsvd_tc_reduce_kernel<<<(unsigned)ceil_div<int64_t>(o4, 256), 256, 0, st>>>(a.partials, o4, a.n_split, out_shift,
+                                                                               s.colsum, Y);
     return check_launch("rsvd_tc_reduce_kernel");
 }
