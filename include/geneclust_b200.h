@@ -95,6 +95,15 @@ int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float *Qin, floa
  * the tensor-core kernel. */
 int gc_rsvd_apply_simt(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *partials,
                        void *stream);
+/* The test matrix Omega of the randomized solver, drawn on the device exactly as scikit-learn draws it on the host
+ * (utils/extmath.py:323-334: random_state.normal(size=(rows, q)) cast to float32): legacy numpy RandomState stream =
+ * MT19937 + polar-method gauss.  mt_state: the 624 MT19937 key words of RandomState(seed).get_state()[1] (device),
+ * mt_pos = get_state()[2].  Writes panel[r*ld + c] for c < q (other columns untouched).  status[0] |= 2 if the
+ * pre-generated word stream held too few accepted polar attempts (caller should fall back / retry; probability ~0).
+ * scratch: gc_mt19937_normal_scratch_bytes(rows, q), 256-byte aligned. */
+int64_t gc_mt19937_normal_scratch_bytes(int64_t rows, int q);
+int gc_mt19937_normal_panel(const uint32_t *mt_state, int mt_pos, int64_t rows, int q, float *panel, int ld,
+                            void *scratch, int32_t *status, void *stream);
 /* Small panel algebra on tall-skinny panels (rows x 64, float32):
  *   gram:  Gm[64 x 64] (float64) = P^T P   (deterministic two-stage reduction; scratch >= gc_gram_scratch_bytes)
  *   right-multiply: Pout = P @ R[64 x 64] (R float32, row-major) */

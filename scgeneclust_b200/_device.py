@@ -277,6 +277,21 @@ class PanelAlgebra:
         return out
 
 
+def device_normal_panel(random_state: int, rows: int, q: int, device) -> torch.Tensor:
+    """`np.random.RandomState(random_state).normal(size=(rows, q)).astype(np.float32)` as a zero-padded rows x 64
+    device panel, generated on the device (gc_mt19937_normal_panel)."""
+    L, st = lib(), stream_handle()
+    state = np.random.RandomState(random_state).get_state()
+    assert state[0] == 'MT19937' and state[3] == 0      # fresh seed: no cached gaussian
+    key = torch.from_numpy(np.ascontiguousarray(state[1], dtype=np.uint32).view(np.int32)).to(device)
+    panel = torch.zeros((rows, Q_LD), dtype=torch.float32, device=device)
+    scratch = torch.empty(L.mt19937_normal_scratch_bytes(rows, q), dtype=torch.uint8, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    L.mt19937_normal_panel(ptr(key), int(state[2]), rows, q, ptr(panel), Q_LD, ptr(scratch), ptr(status), st)
+    panel._gc_status = status           # checked together with the Cholesky status at the end of the solver
+    return panel
+
+
 def pca_solver(n_samples: int, n_features: int, n_comps: int) -> str:
     """sklearn PCA 'auto' policy (decomposition/_pca.py:524-536)."""
     if n_features <= 1000 and n_samples >= 10 * n_features:
@@ -333,12 +348,12 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     # A.shape[1] = length of the Omega rows; trans=0 contracts genes, trans=1 contracts cells
     n_in_total = G_total if fwd == 0 else op.C
 
-    # Omega exactly as sklearn draws it (utils/extmath.py:323-334): normal((A.shape[1], q)) cast to float32
-    omega = np.random.RandomState(random_state).normal(size=(n_in_total, q)).astype(np.float32)
+    # Omega exactly as sklearn draws it (utils/extmath.py:323-334): normal((A.shape[1], q)) cast to float32 - the
+    # legacy RandomState stream is reproduced on the device from the seeded MT19937 state (20-40 ms on the host)
+    Qp = device_normal_panel(random_state, n_in_total, q, dev)
+    omega_status = Qp._gc_status
     if comm is not None and fwd == 0:
-        omega = omega[comm.gene_lo:comm.gene_hi]
-    Qp = torch.zeros((omega.shape[0], Q_LD), dtype=torch.float32, device=dev)
-    Qp[:, :q] = torch.from_numpy(omega).to(dev)
+        Qp = Qp[comm.gene_lo:comm.gene_hi].contiguous()
 
     alg = PanelAlgebra(dev, max(op.C, op.G))
     buf_c = torch.empty((op.C, Q_LD), dtype=torch.float32, device=dev)
@@ -393,8 +408,11 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         base = Bt
     scores = torch.empty((base.shape[0], Q_LD), dtype=torch.float32, device=dev)
     L.panel_matmul(ptr(base), base.shape[0], ptr(uhat), ptr(scores), st)
-    if int(alg.status.item()) != 0:
+    flags = int((alg.status + omega_status).item())
+    if flags & 1:
         raise FloatingPointError("Cholesky-QR panel normalisation hit a non-positive pivot (rank-deficient panel)")
+    if flags & 2:
+        raise RuntimeError("device Omega generation ran out of pre-generated MT19937 words")
     if info is not None:
         info.update(n_iter=n_iter, transpose=bool(transpose), q=q, n_comps=n_comps,
                     singular_values=sing[:n_comps].cpu().numpy(), passes=2 * n_iter + 2)

@@ -39,6 +39,8 @@ SIGNATURES = {
     "gc_rsvd_scratch_bytes": (_i64, [_i64, _i64]),
     "gc_rsvd_apply": (C.c_int, [C.POINTER(ResidualMatrix), C.c_int, _p, _p, C.c_int, _p, _p]),
     "gc_rsvd_apply_simt": (C.c_int, [C.POINTER(ResidualMatrix), C.c_int, _p, _p, C.c_int, _p, _p]),
+    "gc_mt19937_normal_scratch_bytes": (_i64, [_i64, C.c_int]),
+    "gc_mt19937_normal_panel": (C.c_int, [_p, C.c_int, _i64, C.c_int, _p, C.c_int, _p, _p, _p]),
     "gc_gram_scratch_bytes": (_i64, [_i64]),
     "gc_panel_gram": (C.c_int, [_p, _i64, _p, _p, _p]),
     "gc_panel_matmul": (C.c_int, [_p, _i64, _p, _p, _p]),
@@ -63,6 +65,7 @@ SIGNATURES = {
 }
 
 _NO_STATUS = {"gc_abi_version", "gc_last_error", "gc_launch_count", "gc_rsvd_scratch_bytes", "gc_gram_scratch_bytes",
+              "gc_mt19937_normal_scratch_bytes",
               "gc_kmeanspp_scratch_bytes"}
 
 

@@ -229,6 +229,143 @@ kpp_trial_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d, con
     if (threadIdx.x == 0) partial[(int64_t)c * gridDim.x + blockIdx.x] = red[0];
 }
 
+// One greedy round as ONE kernel: every CTA computes its trial-distance tile (as kpp_trial_kernel); the LAST CTA to
+// finish (atomic ticket) then runs the tail of the round that used to be two more launches: candidates_pot = fixed-order
+// sum of the partials, first argmin, new current_pot (kpp_choose_kernel) and - unless this was the last round - the head
+// of the next one (kpp_pick_kernel): adopt the winner's distances, sequential float32 cumsum staged through shared
+// memory, searchsorted of the next uniforms inside shared memory.  Arithmetic and summation orders are unchanged.
+constexpr int kRoundChunk = 6144;     // floats of cumsum staged per pass of the tail (24 KB)
+__global__ void __launch_bounds__(kKppThreads)
+kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t n, int d, int32_t *cand,
+                 float *closest, float *trial_dist, double *partial, const double *__restrict__ uniforms, int n_trials,
+                 int32_t *__restrict__ indices_out, int round, int last_round, unsigned int *ticket) {
+    __shared__ float sc[kDMax];
+    __shared__ double sxx;
+    __shared__ double red[kKppThreads];
+    __shared__ __align__(16) float buf[kRoundChunk];
+    __shared__ float carry;
+    __shared__ int s_best, s_is_last;
+    __shared__ float s_pot;
+    __shared__ double s_rv[32];
+    __shared__ int64_t s_found[32];
+    const int c = blockIdx.y;
+    {
+        const float *xc = X + (int64_t)cand[c] * ldx;
+        if (threadIdx.x < d) sc[threadIdx.x] = xc[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double xx = 0.0;
+            for (int f = 0; f < d; ++f) xx = fma((double)sc[f], (double)sc[f], xx);
+            sxx = xx;
+        }
+        __syncthreads();
+        const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        double v = 0.0;
+        if (i < n) {
+            const float dd = fminf(closest[i], sqdist_upcast(sc, sxx, X + i * ldx, d));
+            trial_dist[(int64_t)c * n + i] = dd;
+            v = (double)dd;
+        }
+        red[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = kKppThreads / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partial[(int64_t)c * gridDim.x + blockIdx.x] = red[0];
+    }
+    // ---- last CTA to finish runs the sequential tail
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y;
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_is_last = (t == total - 1);
+        if (s_is_last) *ticket = 0;              // re-arm for the next launch (stream ordered)
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    const int n_blocks = gridDim.x;
+    // choose: potentials in a fixed order, first argmin
+    if (threadIdx.x < n_trials) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += __ldcg(partial + (int64_t)threadIdx.x * n_blocks + b);
+        red[threadIdx.x] = (double)(float)s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float best_pot = 0.f;
+        int best = 0;
+        for (int t = 0; t < n_trials; ++t) {
+            const float pot = (float)red[t];
+            if (t == 0 || pot < best_pot) { best_pot = pot; best = t; }
+        }
+        st->current_pot = best_pot;
+        st->best = best;
+        s_best = best;
+        s_pot = best_pot;
+        indices_out[round] = cand[best];          // centre chosen in this round
+        carry = 0.f;
+    }
+    __syncthreads();
+    if (last_round) return;
+    // pick for round + 1: closest <- trial_dist[best]; cumsum; searchsorted
+    const float *src = trial_dist + (int64_t)s_best * n;
+    if (threadIdx.x < n_trials) {
+        s_rv[threadIdx.x] = uniforms[(int64_t)round * n_trials + threadIdx.x] * (double)s_pot;
+        s_found[threadIdx.x] = -1;
+    }
+    for (int64_t c0 = 0; c0 < n; c0 += kRoundChunk) {
+        const int cn = (int)min((int64_t)kRoundChunk, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+            const float v = __ldcg(src + c0 + i);
+            buf[i] = v;
+            closest[c0 + i] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // the dependent float32 add chain of np.cumsum (4 cycles per element); the shared-memory loads of the next
+            // 16 elements are issued before the chain of the current 16 so their latency stays off the critical path
+            float acc = carry;
+            int i = 0;
+            float4 *b4 = reinterpret_cast<float4 *>(buf);
+            if (cn >= 16) {
+                float4 a0 = b4[0], a1 = b4[1], a2 = b4[2], a3 = b4[3];
+                for (; i + 16 <= cn; i += 16) {
+                    float4 n0 = a0, n1 = a1, n2 = a2, n3 = a3;
+                    if (i + 32 <= cn) { n0 = b4[(i >> 2) + 4]; n1 = b4[(i >> 2) + 5]; n2 = b4[(i >> 2) + 6]; n3 = b4[(i >> 2) + 7]; }
+                    acc = acc + a0.x; a0.x = acc; acc = acc + a0.y; a0.y = acc; acc = acc + a0.z; a0.z = acc; acc = acc + a0.w; a0.w = acc;
+                    acc = acc + a1.x; a1.x = acc; acc = acc + a1.y; a1.y = acc; acc = acc + a1.z; a1.z = acc; acc = acc + a1.w; a1.w = acc;
+                    acc = acc + a2.x; a2.x = acc; acc = acc + a2.y; a2.y = acc; acc = acc + a2.z; a2.z = acc; acc = acc + a2.w; a2.w = acc;
+                    acc = acc + a3.x; a3.x = acc; acc = acc + a3.y; a3.y = acc; acc = acc + a3.z; a3.z = acc; acc = acc + a3.w; a3.w = acc;
+                    b4[(i >> 2)] = a0; b4[(i >> 2) + 1] = a1; b4[(i >> 2) + 2] = a2; b4[(i >> 2) + 3] = a3;
+                    a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+                }
+            }
+            for (; i < cn; ++i) { acc = acc + buf[i]; buf[i] = acc; }
+            carry = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < n_trials && s_found[threadIdx.x] < 0 && (double)buf[cn - 1] >= s_rv[threadIdx.x]) {
+            // np.searchsorted(cumsum, rv, side='left') restricted to this chunk (earlier chunks are all < rv)
+            const double rv = s_rv[threadIdx.x];
+            int lo = 0, hi = cn;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((double)buf[mid] < rv) lo = mid + 1; else hi = mid;
+            }
+            s_found[threadIdx.x] = c0 + lo;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_trials) {
+        int64_t f = s_found[threadIdx.x];
+        if (f < 0 || f > n - 1) f = n - 1;           // np.clip(candidate_ids, None, n - 1)
+        cand[threadIdx.x] = (int32_t)f;
+    }
+}
+
 // round step C (1 warp): candidates_pot = sum of partials (fixed order), first argmin, new current_pot
 __global__ void kpp_choose_kernel(KppState *st, const double *__restrict__ partial, int n_blocks, int n_trials) {
     if (threadIdx.x == 0) {
@@ -396,7 +533,7 @@ extern "C" int64_t gc_kmeanspp_scratch_bytes(int64_t n, int n_trials) {
     const int64_t n_blocks = ceil_div<int64_t>(n, kKppThreads);
     // state | cand[n_trials] | closest[n] | cumsum[n] | trial_dist[n_trials*n] | partial[n_trials*n_blocks]
     return 256 + 256 + (int64_t)sizeof(float) * (2 * n + (int64_t)n_trials * n) + 256 * 3 +
-           (int64_t)sizeof(double) * n_trials * n_blocks + 256;
+           (int64_t)sizeof(double) * n_trials * n_blocks + 256 + 256 /* ticket */;
 }
 
 extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, int K, int32_t first_center,
@@ -430,19 +567,18 @@ extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, i
         if (int rc = check_launch("kpp_first_kernel")) return rc;
         GC_CUDA(cudaMemcpyAsync(closest, trial, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
     }
-    for (int round = 1; round < K; ++round) {
-        kpp_pick_kernel<<<1, 1024, 0, st>>>(state, closest, trial, n, uniforms, n_trials, cand, cumsum,
-                                            indices_out, round);
+    unsigned int *ticket = (unsigned int *)align((char *)(partial + (int64_t)n_trials * n_blocks));
+    GC_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+    if (K > 1) {
+        // head of round 1 (no winner to adopt yet), then one launch per round
+        kpp_pick_kernel<<<1, 1024, 0, st>>>(state, closest, trial, n, uniforms, n_trials, cand, cumsum, indices_out, 1);
         if (int rc = check_launch("kpp_pick_kernel")) return rc;
         dim3 grid((unsigned)n_blocks, (unsigned)n_trials);
-        kpp_trial_kernel<<<grid, kKppThreads, 0, st>>>(X, ldx, n, d, cand, closest, trial, partial);
-        if (int rc = check_launch("kpp_trial_kernel")) return rc;
-        kpp_choose_kernel<<<1, 32, 0, st>>>(state, partial, n_blocks, n_trials);
-        if (int rc = check_launch("kpp_choose_kernel")) return rc;
-    }
-    if (K > 1) {
-        kpp_finish_kernel<<<1, 32, 0, st>>>(state, cand, indices_out, K);
-        if (int rc = check_launch("kpp_finish_kernel")) return rc;
+        for (int round = 1; round < K; ++round) {
+            kpp_round_kernel<<<grid, kKppThreads, 0, st>>>(state, X, ldx, n, d, cand, closest, trial, partial, uniforms,
+                                                           n_trials, indices_out, round, round == K - 1 ? 1 : 0, ticket);
+            if (int rc = check_launch("kpp_round_kernel")) return rc;
+        }
     }
     gather_rows_kernel<<<K, kDMax, 0, st>>>(X, ldx, indices_out, K, d, centers_out);
     return check_launch("gather_rows_kernel");

@@ -175,3 +175,16 @@ def test_gene_pca_untransposed_shape(torch_cuda, small_counts):
     rel = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
     print(f"gene PCA untransposed: max per-component rel err {rel.max():.2e}")
     assert rel.max() <= 1e-3
+
+
+@pytest.mark.parametrize("seed,rows,q", [(0, 20000, 60), (7, 1237, 60), (123456, 50, 13), (2 ** 32 - 1, 3000, 60)])
+def test_device_omega_equals_numpy_randomstate(torch_cuda, seed, rows, q):
+    """The randomized solver's test matrix (sklearn utils/extmath.py:323-334) generated on the device from the seeded
+    MT19937 state must be the float32 cast of numpy's own legacy stream: identical entries, zero padding columns."""
+    from scgeneclust_b200._device import device_normal_panel
+    panel = device_normal_panel(seed, rows, q, "cuda")
+    assert int(panel._gc_status.item()) == 0
+    got = panel.cpu().numpy()
+    ref = np.random.RandomState(seed).normal(size=(rows, q)).astype(np.float32)
+    assert np.array_equal(got[:, :q], ref)
+    assert not got[:, q:].any()
