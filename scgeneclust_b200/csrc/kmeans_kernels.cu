@@ -6,98 +6,134 @@
 namespace gc {
 
 constexpr int kDMax = 64;        // feature dimension bound (GeneClust uses 50 PCs)
-constexpr int kAssignThreads = 64;
 
 // ---------------------------------------------------------------------------------------------------------
-// assignment: one thread per sample, centres staged in shared memory (K*d floats + K norms)
+// assignment: one WARP per sample; lane l scores centres l, l+32, ... (centres staged in shared memory with a padded
+// row stride, so the 32 lanes read 32 different banks), then a warp arg-min with first-index ties.
 // labels = argmin_j (|c_j|^2 - 2 x.c_j), strict '<' => first index on ties (_k_means_lloyd.pyx:196-211)
 // sqdist = sum (x-c)^2 in the 4-way unrolled order of _euclidean_dense_dense (_k_means_common.pyx:16-43)
+// The float32 operation order of every (sample, centre) score is the one of the original one-thread-per-sample
+// kernel (two interleaved fma chains, one fma with the norm): results are bit-identical to it.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAssignThreads)
+constexpr int kAssignWarps = 8;
+__global__ void __launch_bounds__(kAssignWarps * 32)
 kmeans_assign_kernel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ gather, int64_t n,
-                     const float *__restrict__ centers, int K, int d, int32_t *__restrict__ labels,
-                     float *__restrict__ sqdist) {
+                     const float *__restrict__ centers, int K, int d, int ds /* padded row stride, odd */,
+                     int32_t *__restrict__ labels, float *__restrict__ sqdist) {
     extern __shared__ float smem[];
-    float *sc = smem;            // K * d
-    float *sn = smem + K * d;    // K
-    for (int i = threadIdx.x; i < K * d; i += blockDim.x) sc[i] = centers[i];
+    float *sc = smem;             // K * ds
+    float *sn = smem + K * ds;    // K
+    for (int i = threadIdx.x; i < K * d; i += blockDim.x) sc[(i / d) * ds + (i % d)] = centers[i];
     __syncthreads();
     for (int j = threadIdx.x; j < K; j += blockDim.x) {
         float s = 0.f;
-        for (int f = 0; f < d; ++f) s = fmaf(sc[j * d + f], sc[j * d + f], s);
+        for (int f = 0; f < d; ++f) s = fmaf(sc[j * ds + f], sc[j * ds + f], s);
         sn[j] = s;
     }
     __syncthreads();
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const int64_t row = gather ? gather[s] : s;
-    const float *xp = X + row * ldx;
-    float x[kDMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t s = (int64_t)blockIdx.x * kAssignWarps + warp; s < n; s += (int64_t)gridDim.x * kAssignWarps) {
+        const int64_t row = gather ? gather[s] : s;
+        const float *xp = X + row * ldx;
+        float x[kDMax];
 #pragma unroll
-    for (int f = 0; f < kDMax; ++f) x[f] = f < d ? xp[f] : 0.f;
+        for (int f = 0; f < kDMax; ++f) x[f] = f < d ? __ldg(xp + f) : 0.f;   // same address in all lanes: broadcast
 
-    float best = 0.f;
-    int lab = 0;
-    for (int j = 0; j < K; ++j) {
-        const float *c = sc + j * d;
-        float dot0 = 0.f, dot1 = 0.f;
+        float best = 0.f;
+        int lab = -1;
+        for (int j = lane; j < K; j += 32) {
+            const float *c = sc + j * ds;
+            float dot0 = 0.f, dot1 = 0.f;
 #pragma unroll
-        for (int f = 0; f < kDMax; f += 2) {
-            if (f < d) dot0 = fmaf(x[f], c[f], dot0);
-            if (f + 1 < d) dot1 = fmaf(x[f + 1], c[f + 1], dot1);
+            for (int f = 0; f < kDMax; f += 2) {
+                if (f < d) dot0 = fmaf(x[f], c[f], dot0);
+                if (f + 1 < d) dot1 = fmaf(x[f + 1], c[f + 1], dot1);
+            }
+            const float pd = fmaf(-2.0f, dot0 + dot1, sn[j]);
+            if (lab < 0 || pd < best) { best = pd; lab = j; }     // ascending j within the lane: first index on ties
         }
-        const float pd = fmaf(-2.0f, dot0 + dot1, sn[j]);
-        if (j == 0 || pd < best) { best = pd; lab = j; }
-    }
-    labels[s] = lab;
-    if (sqdist != nullptr) {
-        const float *c = sc + lab * d;
-        float result = 0.f;
-        const int n4 = d / 4;
+        // warp arg-min, ties -> smaller index (lanes without a centre carry lab = -1)
 #pragma unroll
-        for (int i = 0; i < kDMax / 4; ++i) {
-            if (i < n4) {
-                const float t0 = x[4 * i] - c[4 * i], t1 = x[4 * i + 1] - c[4 * i + 1];
-                const float t2 = x[4 * i + 2] - c[4 * i + 2], t3 = x[4 * i + 3] - c[4 * i + 3];
-                result = result + (((t0 * t0 + t1 * t1) + t2 * t2) + t3 * t3);
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, lab, o);
+            if (ol >= 0 && (lab < 0 || ob < best || (ob == best && ol < lab))) { best = ob; lab = ol; }
+        }
+        if (lane == 0) {
+            labels[s] = lab;
+            if (sqdist != nullptr) {
+                const float *c = sc + lab * ds;
+                float result = 0.f;
+                const int n4 = d / 4;
+#pragma unroll
+                for (int i = 0; i < kDMax / 4; ++i) {
+                    if (i < n4) {
+                        const float t0 = x[4 * i] - c[4 * i], t1 = x[4 * i + 1] - c[4 * i + 1];
+                        const float t2 = x[4 * i + 2] - c[4 * i + 2], t3 = x[4 * i + 3] - c[4 * i + 3];
+                        result = result + (((t0 * t0 + t1 * t1) + t2 * t2) + t3 * t3);
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < kDMax; ++f) {
+                    if (f >= 4 * n4 && f < d) { const float t = x[f] - c[f]; result = result + t * t; }
+                }
+                sqdist[s] = result;
             }
         }
-#pragma unroll
-        for (int f = 0; f < kDMax; ++f) {
-            if (f >= 4 * n4 && f < d) { const float t = x[f] - c[f]; result = result + t * t; }
-        }
-        sqdist[s] = result;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// minibatch centre update: one CTA per cluster, thread f owns feature f, samples visited in batch order
-// (_k_means_minibatch.pyx:60-108 with unit sample weights)
+// minibatch centre update: one warp per cluster, lane l owns features l and l + 32; the batch labels are scanned 32
+// at a time (coalesced load + ballot) and the matching samples are accumulated in batch order
+// (_k_means_minibatch.pyx:60-108 with unit sample weights: sequential float32 accumulation in sample order)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kDMax)
+__global__ void __launch_bounds__(32)
 kmeans_minibatch_update_kernel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ gather,
                                int64_t n, const int32_t *__restrict__ labels,
                                const float *__restrict__ centers_old, float *__restrict__ centers_new,
                                float *__restrict__ weight_sums, int K, int d) {
-    const int k = blockIdx.x, f = threadIdx.x;
-    float wsum = 0.f;
+    extern __shared__ int32_t hits[];          // rows of this cluster's samples, in batch order (<= n entries)
+    const int k = blockIdx.x, lane = threadIdx.x;
+    const int f0 = lane, f1 = lane + 32;
     const float w_old = weight_sums[k];
-    float acc = f < d ? centers_old[k * d + f] * w_old : 0.f;
-    for (int64_t s = 0; s < n; ++s) {
-        if (labels[s] == k) {              // warp-uniform
-            wsum += 1.0f;
-            const int64_t row = gather ? gather[s] : s;
-            if (f < d) acc = acc + X[row * ldx + f];
-        }
+    float acc0 = f0 < d ? centers_old[k * d + f0] * w_old : 0.f;
+    float acc1 = f1 < d ? centers_old[k * d + f1] * w_old : 0.f;
+    // pass 1: compact the matching batch positions (independent coalesced loads, unrolled so their latencies overlap)
+    int cnt = 0;
+#pragma unroll 4
+    for (int64_t s0 = 0; s0 < n; s0 += 32) {
+        const int64_t s = s0 + lane;
+        const bool hit = s < n && __ldg(labels + s) == k;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) hits[cnt + __popc(m & ((1u << lane) - 1u))] = gather ? __ldg(gather + s) : (int32_t)s;
+        cnt += __popc(m);
     }
-    __syncthreads();  // every thread has read weight_sums[k] before it is overwritten
-    if (wsum > 0.f) {
-        const float w_new = w_old + wsum;
+    __syncwarp();
+    // pass 2: sequential float32 accumulation in batch order; the row loads of four samples are issued together
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) {
+        const int64_t r0 = hits[j], r1 = hits[j + 1], r2 = hits[j + 2], r3 = hits[j + 3];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        if (f0 < d) { a0 = X[r0 * ldx + f0]; a1 = X[r1 * ldx + f0]; a2 = X[r2 * ldx + f0]; a3 = X[r3 * ldx + f0]; }
+        if (f1 < d) { b0 = X[r0 * ldx + f1]; b1 = X[r1 * ldx + f1]; b2 = X[r2 * ldx + f1]; b3 = X[r3 * ldx + f1]; }
+        acc0 = acc0 + a0; acc0 = acc0 + a1; acc0 = acc0 + a2; acc0 = acc0 + a3;
+        acc1 = acc1 + b0; acc1 = acc1 + b1; acc1 = acc1 + b2; acc1 = acc1 + b3;
+    }
+    for (; j < cnt; ++j) {
+        const int64_t r = hits[j];
+        if (f0 < d) acc0 = acc0 + X[r * ldx + f0];
+        if (f1 < d) acc1 = acc1 + X[r * ldx + f1];
+    }
+    if (cnt > 0) {
+        const float w_new = w_old + (float)cnt;      // = w_old + 1 + 1 + ... exactly: counts stay far below 2^24
         const float alpha = 1.0f / w_new;
-        if (f < d) centers_new[k * d + f] = acc * alpha;
-        if (f == 0) weight_sums[k] = w_new;
-    } else if (f < d) {
-        centers_new[k * d + f] = centers_old[k * d + f];
+        if (f0 < d) centers_new[k * d + f0] = acc0 * alpha;
+        if (f1 < d) centers_new[k * d + f1] = acc1 * alpha;
+        if (lane == 0) weight_sums[k] = w_new;
+    } else {
+        if (f0 < d) centers_new[k * d + f0] = centers_old[k * d + f0];
+        if (f1 < d) centers_new[k * d + f1] = centers_old[k * d + f1];
     }
 }
 
@@ -287,10 +323,12 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t
     __threadfence();
     const int n_blocks = gridDim.x;
     // choose: potentials in a fixed order, first argmin
-    if (threadIdx.x < n_trials) {
+    for (int t = threadIdx.x >> 5; t < n_trials; t += kKppThreads / 32) {   // one warp per trial, fixed reduction tree
         double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += __ldcg(partial + (int64_t)threadIdx.x * n_blocks + b);
-        red[threadIdx.x] = (double)(float)s;
+        for (int b = threadIdx.x & 31; b < n_blocks; b += 32) s += __ldcg(partial + (int64_t)t * n_blocks + b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) red[t] = (double)(float)s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -472,15 +510,18 @@ extern "C" int gc_kmeans_assign(const float *X, int64_t ldx, const int32_t *gath
     GC_REQUIRE(X && centers && labels, "null pointer");
     GC_REQUIRE(d >= 1 && d <= kDMax, "d must be in [1, 64]");
     GC_REQUIRE(K >= 1 && n >= 1 && ldx >= d, "bad shape");
-    const size_t smem = (size_t)(K * d + K) * sizeof(float);
+    const int ds = d | 1;                                            // odd row stride: conflict-free lane-per-centre reads
+    const size_t smem = (size_t)(K * ds + K) * sizeof(float);
     GC_REQUIRE(smem <= 200 * 1024, "K*d too large for the shared-memory centre cache");
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         GC_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kmeans_assign_kernel<<<(unsigned)ceil_div<int64_t>(n, kAssignThreads), kAssignThreads, smem, as_stream(stream)>>>(
-        X, ldx, gather, n, centers, K, d, labels, sqdist);
+    // every CTA stages the centres once: a few samples per warp amortise that without starving the SMs
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(n, kAssignWarps), (int64_t)kNumSMs * 4));
+    kmeans_assign_kernel<<<(unsigned)ctas, kAssignWarps * 32, smem, as_stream(stream)>>>(X, ldx, gather, n, centers, K, d, ds,
+                                                                                     labels, sqdist);
     return check_launch("kmeans_assign_kernel");
 }
 
@@ -489,7 +530,14 @@ extern "C" int gc_kmeans_minibatch_update(const float *X, int64_t ldx, const int
                                           float *weight_sums, int K, int d, void *stream) {
     GC_REQUIRE(X && labels && centers_old && centers_new && weight_sums, "null pointer");
     GC_REQUIRE(d >= 1 && d <= kDMax && K >= 1 && n >= 1, "bad shape");
-    kmeans_minibatch_update_kernel<<<K, kDMax, 0, as_stream(stream)>>>(X, ldx, gather, n, labels, centers_old,
+    const size_t hit_bytes = (size_t)n * 4;
+    GC_REQUIRE(hit_bytes <= 200 * 1024, "mini-batch larger than 51200 samples");
+    static thread_local size_t upd_configured = 0;
+    if (hit_bytes > 48 * 1024 && hit_bytes > upd_configured) {
+        GC_CUDA(cudaFuncSetAttribute(kmeans_minibatch_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hit_bytes));
+        upd_configured = hit_bytes;
+    }
+    kmeans_minibatch_update_kernel<<<K, 32, hit_bytes, as_stream(stream)>>>(X, ldx, gather, n, labels, centers_old,
                                                                       centers_new, weight_sums, K, d);
     return check_launch("kmeans_minibatch_update_kernel");
 }

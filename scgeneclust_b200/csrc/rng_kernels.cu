@@ -31,40 +31,47 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 }
 
 // One CTA: emits n_words tempered outputs starting at position `pos` (0..624; 624 = regenerate first) of `state`.
+// The 624-word block is regenerated in three dependent phases ([0,227), [227,454), [454,624)) into the other of two
+// buffers (old values are read from the current one, so a phase needs no read/write fence of its own): three
+// __syncthreads per 624 words, and every thread tempers and stores the word it has just produced.
 __global__ void __launch_bounds__(256)
 mt19937_stream_kernel(const uint32_t *__restrict__ state, int pos, int64_t n_words, uint32_t *__restrict__ out) {
-    __shared__ uint32_t mt[kMtN];
+    __shared__ uint32_t buf[2][kMtN];
     const int t = threadIdx.x;
-    for (int i = t; i < kMtN; i += blockDim.x) mt[i] = state[i];
+    for (int i = t; i < kMtN; i += blockDim.x) buf[0][i] = state[i];
     __syncthreads();
     int64_t done = 0;
-    // words left in the current block
-    if (pos < kMtN) {
+    if (pos < kMtN) {          // words left in the current block
         const int avail = kMtN - pos;
-        for (int i = t; i < avail && i < n_words; i += blockDim.x) out[i] = mt_temper(mt[pos + i]);
+        for (int i = t; i < avail && i < n_words; i += blockDim.x) out[i] = mt_temper(buf[0][pos + i]);
         done = min((int64_t)avail, n_words);
     }
+    int cur = 0;
     while (done < n_words) {
-        // regenerate the 624-word block: phases [0,227) [227,454) [454,623) {623}; each reads, syncs, writes
-        uint32_t v;
-        if (t < 227) v = mt_twist(mt[t], mt[t + 1], mt[t + kMtM]);
+        const uint32_t *mt = buf[cur];
+        uint32_t *nt = buf[cur ^ 1];
+        const int64_t left = n_words - done;
+        if (t < 227) {
+            const uint32_t v = mt_twist(mt[t], mt[t + 1], mt[t + kMtM]);
+            nt[t] = v;
+            if (t < left) out[done + t] = mt_temper(v);
+        }
         __syncthreads();
-        if (t < 227) mt[t] = v;
+        if (t < 227) {
+            const uint32_t v = mt_twist(mt[t + 227], mt[t + 228], nt[t]);
+            nt[t + 227] = v;
+            if (t + 227 < left) out[done + t + 227] = mt_temper(v);
+        }
         __syncthreads();
-        if (t < 227) v = mt_twist(mt[t + 227], mt[t + 228], mt[t]);
+        if (t < 170) {         // kk = 454 + t; the last word (kk = 623) wraps to the NEW word 0
+            const uint32_t nxt = t < 169 ? mt[t + 455] : nt[0];
+            const uint32_t v = mt_twist(mt[t + 454], nxt, nt[t + 227]);
+            nt[t + 454] = v;
+            if (t + 454 < left) out[done + t + 454] = mt_temper(v);
+        }
         __syncthreads();
-        if (t < 227) mt[t + 227] = v;
-        __syncthreads();
-        if (t < 169) v = mt_twist(mt[t + 454], mt[t + 455], mt[t + 227]);
-        __syncthreads();
-        if (t < 169) mt[t + 454] = v;
-        __syncthreads();
-        if (t == 0) mt[623] = mt_twist(mt[623], mt[0], mt[396]);
-        __syncthreads();
-        const int64_t take = min((int64_t)kMtN, n_words - done);
-        for (int i = t; i < take; i += blockDim.x) out[done + i] = mt_temper(mt[i]);
-        done += take;
-        // the next block's first phase reads mt[] entries written above only after the syncs of its own phases
+        done += min((int64_t)kMtN, left);
+        cur ^= 1;
     }
 }
 

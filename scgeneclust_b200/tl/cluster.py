@@ -45,7 +45,8 @@ class DeviceMiniBatchKMeans:
         n_trials = 2 + int(np.log(K))
         sw = np.ones(ns, dtype=np.float32)
         first = int(rs.choice(ns, p=sw / sw.sum()))
-        uniforms = np.stack([rs.uniform(size=n_trials) for _ in range(K - 1)]) if K > 1 else np.zeros((0, n_trials))
+        # one call draws the same stream as the K-1 per-round `uniform(size=n_trials)` calls of _kmeans_plusplus
+        uniforms = rs.uniform(size=(K - 1, n_trials)) if K > 1 else np.zeros((0, n_trials))
         d_uni = torch.from_numpy(np.ascontiguousarray(uniforms)).to(X.device)
         ws = torch.empty(L.kmeanspp_scratch_bytes(ns, n_trials), dtype=torch.uint8, device=X.device)
         centers = torch.empty((K, d), dtype=torch.float32, device=X.device)
@@ -79,15 +80,27 @@ class DeviceMiniBatchKMeans:
 
         ewa, ewa_min, no_improvement, n_since_reassign = None, None, 0, 0
         n_steps = (self.max_iter * n) // batch
+        # `random_state.choice(n, batch, p=sample_weight / sum)` (cluster/_kmeans.py:2169-2174) is, for replace=True
+        # with p, `cdf.searchsorted(random_sample(batch), side='right')` with cdf = float64 cumsum of p normalised by
+        # its last entry (numpy mtrand.pyx RandomState.choice); the cdf is the same every step, so it is built once
         p = np.ones(n, dtype=np.float32)
         p = p / np.sum(p)
+        cdf = np.asarray(p, dtype=np.float64).cumsum()
+        cdf /= cdf[-1]
         labels_b = torch.empty(batch, dtype=torch.int32, device=dev)
         sq_b = torch.empty(batch, dtype=torch.float32, device=dev)
         inertia_d = torch.empty(1, dtype=torch.float64, device=dev)
+        idx = torch.empty(batch, dtype=torch.int32, device=dev)
+        # pinned staging: one upload and one (two-part) read-back per step, a single stream synchronisation
+        idx_pin = torch.empty(batch, dtype=torch.int32).pin_memory()
+        counts_pin = torch.empty(K, dtype=torch.float32).pin_memory()
+        inertia_pin = torch.empty(1, dtype=torch.float64).pin_memory()
+        stream = torch.cuda.current_stream()
         step = 0
         for step in range(n_steps):
-            idx_h = rs.choice(n, batch, p=p, replace=True)
-            idx = torch.from_numpy(idx_h.astype(np.int32)).to(dev, non_blocking=True)
+            idx_h = cdf.searchsorted(rs.random_sample(batch), side='right')
+            idx_pin.numpy()[:] = idx_h
+            idx.copy_(idx_pin, non_blocking=True)
             # _random_reassign(), evaluated before the step on the counts of the previous one
             n_since_reassign += batch
             random_reassign = bool((counts_h == 0).any() or n_since_reassign >= 10 * K)
@@ -98,8 +111,11 @@ class DeviceMiniBatchKMeans:
             L.sum_f32(ptr(sq_b), batch, ptr(inertia_d), st)
             L.kmeans_minibatch_update(ptr(X), X.stride(0), ptr(idx), batch, ptr(labels_b), ptr(centers),
                                       ptr(centers_new), ptr(counts), K, d, st)
-            counts_h = counts.cpu().numpy()
-            batch_inertia = float(np.float32(inertia_d.item()))
+            counts_pin.copy_(counts, non_blocking=True)
+            inertia_pin.copy_(inertia_d, non_blocking=True)
+            stream.synchronize()
+            counts_h = counts_pin.numpy().copy()
+            batch_inertia = float(np.float32(inertia_pin.numpy()[0]))
             if random_reassign and self.reassignment_ratio > 0:
                 to_reassign = counts_h < self.reassignment_ratio * counts_h.max()
                 if to_reassign.sum() > 0.5 * batch:
@@ -110,9 +126,11 @@ class DeviceMiniBatchKMeans:
                     picks = rs.choice(batch, replace=False, size=n_reassigns)
                     rows = torch.from_numpy(idx_h[picks].astype(np.int64)).to(dev)
                     centers_new[torch.from_numpy(np.flatnonzero(to_reassign)).to(dev)] = X.index_select(0, rows)
-                counts_h = counts_h.copy()
-                counts_h[to_reassign] = np.min(counts_h[~to_reassign])
-                counts.copy_(torch.from_numpy(counts_h))
+                    # the "dirty hack" count reset of _mini_batch_step (cluster/_kmeans.py:1679-1682); a no-op without
+                    # reassigned centres
+                    counts_h[to_reassign] = np.min(counts_h[~to_reassign])
+                    counts_pin.numpy()[:] = counts_h
+                    counts.copy_(counts_pin, non_blocking=True)
             centers, centers_new = centers_new, centers
             # _mini_batch_convergence (tol == 0)
             batch_inertia /= batch

@@ -50,14 +50,25 @@ def _isolation_forest_outliers(values: np.ndarray, random_state: int) -> np.ndar
     return IsolationForest(random_state=random_state).fit_predict(values.reshape(-1, 1)) == -1
 
 
+def _first_extremes_per_cluster(cluster: np.ndarray, value: np.ndarray):
+    """Positions of the first maximum and of the first minimum of `value` inside every cluster, ascending cluster id -
+    what `groupby('cluster')[col].nlargest(1)` / `.nsmallest(1)` (keep='first') pick.  One stable sort by cluster
+    (original order inside a cluster) serves both."""
+    order = np.argsort(cluster, kind='stable')
+    c, v = cluster[order], value[order]
+    starts = np.flatnonzero(np.r_[True, c[1:] != c[:-1]])
+    seg = np.repeat(np.arange(len(starts)), np.diff(np.r_[starts, len(c)]))
+    out = []
+    for reduce_ in (np.maximum, np.minimum):
+        ext = reduce_.reduceat(v, starts)
+        hit = np.flatnonzero(v == ext[seg])                       # sorted positions attaining the extreme
+        out.append(order[hit[np.r_[True, seg[hit][1:] != seg[hit][:-1]]]])
+    return out[0], out[1]
+
+
 def _first_extreme_per_cluster(cluster: np.ndarray, value: np.ndarray, largest: bool) -> np.ndarray:
-    """Positions of the first maximum (or minimum) of `value` inside every cluster, ascending cluster id - what
-    `groupby('cluster')[col].nlargest(1)` / `.nsmallest(1)` (keep='first') pick."""
-    key = -value if largest else value
-    order = np.lexsort((np.arange(len(value)), key, cluster))   # by cluster, then key, then original position
-    first = np.ones(len(order), bool)
-    first[1:] = cluster[order][1:] != cluster[order][:-1]
-    return order[first]
+    first_max, first_min = _first_extremes_per_cluster(cluster, value)
+    return first_max if largest else first_min
 
 
 def select_from_clusters(adata, version: Literal['fast', 'ps'], post_hoc_filtering: bool = True,
@@ -82,8 +93,8 @@ def select_from_clusters(adata, version: Literal['fast', 'ps'], post_hoc_filteri
             outlier_genes = np.array([])
         pos = np.flatnonzero(~is_single)
         closeness = adata.var['closeness'].to_numpy()[pos]
-        max_genes = var_names[pos[_first_extreme_per_cluster(cluster[pos], closeness, True)]]
-        min_genes = var_names[pos[_first_extreme_per_cluster(cluster[pos], closeness, False)]]
+        first_max, first_min = _first_extremes_per_cluster(cluster[pos], closeness)
+        max_genes, min_genes = var_names[pos[first_max]], var_names[pos[first_min]]
         return np.hstack((max_genes, min_genes, outlier_genes))
     is_low_density = cluster == -1
     if (n_low := int(is_low_density.sum())) > 0:

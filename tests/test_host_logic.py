@@ -111,3 +111,21 @@ def test_redundancy_mst_is_max_spanning_forest():
             tot += w
     assert np.isclose(R[edges[:, 0], edges[:, 1]].sum(), tot, rtol=0, atol=1e-12)
     assert list(map(tuple, edges)) == sorted(map(tuple, edges))
+
+
+def test_minibatch_sampling_restatement_equals_randomstate_choice():
+    """DeviceMiniBatchKMeans draws its mini-batches as `cdf.searchsorted(rs.random_sample(batch), 'right')` with a cdf
+    built once; that must be the index stream of `rs.choice(n, batch, p=p)` (sklearn cluster/_kmeans.py:2169-2174),
+    and one `uniform(size=(K-1, t))` call must equal the K-1 per-round draws of k-means++ (cluster/_kmeans.py:249)."""
+    import numpy as np
+    for seed, n, batch in [(0, 20000, 2000), (3, 1371, 1024), (11, 50, 50)]:
+        p = np.ones(n, dtype=np.float32)
+        p = p / np.sum(p)
+        cdf = np.asarray(p, dtype=np.float64).cumsum()
+        cdf /= cdf[-1]
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        for _ in range(5):
+            assert np.array_equal(a.choice(n, batch, p=p, replace=True), cdf.searchsorted(b.random_sample(batch), side='right'))
+        assert a.randint(1 << 30) == b.randint(1 << 30)          # both streams consumed the same amount
+    a, b = np.random.RandomState(5), np.random.RandomState(5)
+    assert np.array_equal(np.stack([a.uniform(size=7) for _ in range(9)]), b.uniform(size=(9, 7)))
