@@ -13,19 +13,20 @@
 // (measured: tf32 2e-3, bf16 O(1); hi+lo 8e-5).  The Q panel is pre-split once per pass (tiny, L2 resident).
 //
 // CTA = one 128-row output tile x one k-slab (split-K; slabs are reduced in a fixed order by a second kernel, so
-// results are deterministic), one CTA per SM, 608 threads:
-//   warps 0-15  producers (then epilogue): raw count tile (shared memory) -> residual math -> bf16 hi/lo UMMA tile
+// results are deterministic), one CTA per SM, 576 threads:
+//   warps 0-15  producers (then epilogue), organised as FOUR GROUPS of four warps: group g owns the stages it = g, g+4,
+//               ... completely (128 rows x 64 k = 8 chunks of 8 entries per thread).  A group pays the per-stage fixed
+//               costs (proxy fence, barrier round trips) once per 64 entries per thread, and the groups drift apart in
+//               time, so one group's fence / wait bubbles are filled by the other groups' math (with all sixteen warps
+//               on the same stage - the previous layout - every warp hit the same bubble at the same time).
+//               Counts come straight from HBM into registers, prefetched one whole group-stage (= four stages of the
+//               CTA) ahead: 64 KB of reads in flight per SM.
 //   warp 16     MMA issuer + TMEM owner
 //   warp 17     bulk-copy issuer for the panel tiles (Qh/Ql, stored PRE-SWIZZLED per 64-row tile by the prep kernel, so
 //               one 8 KB cp.async.bulk lands a tile in the UMMA SWIZZLE_128B layout)
-//   warp 18     TMA issuer for the raw count tiles (2-D tensor map over the uint16 matrix, zero fill out of bounds)
-//               and the 64 per-stage constants (s_g/T or r_c)
-// Two shared-memory rings: 5 raw stages (16 KB counts + 256 B constants; 80 KB of HBM reads in flight per SM with no
-// registers or address arithmetic spent on them) and 3 UMMA stages of 48 KB (A hi, A lo, B hi, B lo).
+// Four UMMA stages of 48 KB (A hi, A lo, B hi, B lo): the slot a group needs was last used by its own previous stage.
 // Bound: HBM (algorithmic 2 B/entry); the producer ALU work (12 lane-instructions per entry) is the practical limiter.
-#include <cuda.h>
 #include <cuda_bf16.h>
-#include <cudaTypedefs.h>
 
 #include "common.cuh"
 
@@ -34,29 +35,26 @@ namespace gc {
 constexpr int TC_TM = 128;           // output rows per CTA (UMMA M)
 constexpr int TC_TN = 64;            // panel width (UMMA N)
 constexpr int TC_TK = 64;            // k per stage (one 128-byte swizzle row of bf16)
-constexpr int TC_STAGES = 3;         // UMMA operand stages
-constexpr int TC_RAW_STAGES = 5;     // raw count stages
+constexpr int TC_STAGES = 4;         // UMMA operand stages = producer groups
+constexpr int TC_GROUPS = 4;
 constexpr int TC_PRODUCER_WARPS = 16;
+constexpr int TC_GROUP_WARPS = TC_PRODUCER_WARPS / TC_GROUPS;
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
-constexpr int TC_THREADS = TC_PRODUCERS + 96;
+constexpr int TC_THREADS = TC_PRODUCERS + 64;
+constexpr int TC_CHUNKS = 8;         // 16-byte count chunks per producer thread and stage
 constexpr int TC_A_BYTES = TC_TM * TC_TK * 2;      // 16 KB per half (hi or lo)
 constexpr int TC_B_BYTES = TC_TN * TC_TK * 2;      // 8 KB per half
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
-constexpr int TC_RAW_TILE_BYTES = TC_TM * TC_TK * 2;              // 16 KB of uint16 counts
-constexpr int TC_RAW_BYTES = TC_RAW_TILE_BYTES + TC_TK * 4;       // + 64 float constants
 constexpr int TC_BAR_BYTES = 256;
-// TMEM: two accumulator sets (k-slice parity) x {D1: 128 columns = [A_hi Q_hi | A_hi Q_lo], D2: 64 columns = A_lo Q_hi}.
-// Back-to-back MMAs into ONE accumulator serialise on its read-modify-write (~120 cycles each at N = 64, measured);
-// with four independent accumulators and the hi.hi / hi.lo products fused into one N = 128 MMA they pipeline.
+// TMEM: two accumulator sets (k-slice parity) x {D1: 128 columns = [A_hi Q_hi | A_hi Q_lo], D2: 64 columns = A_lo Q_hi}:
+// the hi.hi and hi.lo products are one N = 128 MMA (64 cycles, full rate; N = 64 runs at 48 cycles, 67 %).
 constexpr int TC_TMEM_SET = 192, TC_TMEM_COLS = 512;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_RAW_STAGES * TC_RAW_BYTES + 1024 /*align*/ + TC_BAR_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + TC_BAR_BYTES;
 
 struct TcArgs {
     const uint16_t *counts; int64_t C, G, ld;
     const float *rpad;                   // [ceil128(C)]  r_c  (1.0 beyond C)
     const float *tpad;                   // [ceil128(ld)] s_g / T (1.0 beyond G)
-    const float *tperm;                  // tpad with every 64-block permuted for conflict-free shared-memory reads:
-                                         // gene 8a + 4h + j of a block sits at h*32 + a*4 + j
     float inv_theta, clip;
     uint32_t magic;                      // 0x4B000000 (2^23) as a run-time value: keeps it in a register so that PRMT
                                          // takes its selector as the immediate (ptxas otherwise re-materialises it)
@@ -81,21 +79,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// 2-D tiled tensor copy global -> shared (TMA), coordinates {c0 = innermost (column), c1 = row}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int32_t c0, int32_t c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds32f(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -266,8 +249,7 @@ __global__ void __launch_bounds__(256)
 tc_prep_kernel(const float *__restrict__ Q, int64_t n_k, int64_t n_k_pad, const float *__restrict__ k_shift,
                __nv_bfloat16 *__restrict__ Qh, __nv_bfloat16 *__restrict__ Ql, double *__restrict__ colsum_part,
                const float *__restrict__ row_sum_f, int64_t C, int64_t C_pad, const float *__restrict__ col_sum_f,
-               int64_t G, int64_t G_pad, float inv_total, float *__restrict__ rpad, float *__restrict__ tpad,
-               float *__restrict__ tperm) {
+               int64_t G, int64_t G_pad, float inv_total, float *__restrict__ rpad, float *__restrict__ tpad) {
     __shared__ double red[16][128];
     const int rl = threadIdx.x >> 4, cg = threadIdx.x & 15;
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
@@ -308,12 +290,8 @@ tc_prep_kernel(const float *__restrict__ Q, int64_t n_k, int64_t n_k_pad, const 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C_pad; i += stride)
         rpad[i] = i < C ? row_sum_f[i] : 1.0f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < G_pad; i += stride) {
-        const float t = i < G ? col_sum_f[i] * inv_total : 1.0f;
-        tpad[i] = t;
-        const int w = (int)(i & 63);                       // 8a + 4h + j  ->  h*32 + a*4 + j
-        tperm[(i & ~(int64_t)63) + ((w >> 2) & 1) * 32 + (w >> 3) * 4 + (w & 3)] = t;
-    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < G_pad; i += stride)
+        tpad[i] = i < G ? col_sum_f[i] * inv_total : 1.0f;
 }
 
 // colsum[0..63] = sum_k Q[k,:], colsum[64..127] = sum_k k_shift[k] Q[k,:]   (fixed block order => deterministic)
@@ -328,14 +306,12 @@ __global__ void tc_colsum_kernel(const double *__restrict__ part, int n_blocks, 
 // ---------------------------------------------------------------------------------------------------------
 template <int TRANS, bool LO_CLIP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-rsvd_apply_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+rsvd_apply_tc_kernel(const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t raw_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-    const uint32_t bar_base = raw_base + TC_RAW_STAGES * TC_RAW_BYTES;
-    // barriers (8 B each): full[S] | empty[S] | raw_full[R] | raw_empty[R] | accum ; then the TMEM address slot
-    const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * TC_STAGES, bar_rfull = bar_empty + 8 * TC_STAGES,
-                   bar_rempty = bar_rfull + 8 * TC_RAW_STAGES, bar_accum = bar_rempty + 8 * TC_RAW_STAGES;
+    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    // barriers (8 B each): full[S] | empty[S] | accum ; then the TMEM address slot
+    const uint32_t bar_full = bar_base, bar_empty = bar_full + 8 * TC_STAGES, bar_accum = bar_empty + 8 * TC_STAGES;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (bar_accum + 8 - smem_base));
 
@@ -348,12 +324,8 @@ rsvd_apply_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     if (warp == TC_PRODUCER_WARPS) {
         if (lane == 0) {
             for (int s = 0; s < TC_STAGES; ++s) {
-                mbar_init(bar_full + 8 * s, TC_PRODUCER_WARPS + 1);   // one arrive per producer warp + the panel copier
+                mbar_init(bar_full + 8 * s, TC_GROUP_WARPS + 1);      // one arrive per warp of the owning group + the panel copier
                 mbar_init(bar_empty + 8 * s, 1);                      // tcgen05.commit
-            }
-            for (int s = 0; s < TC_RAW_STAGES; ++s) {
-                mbar_init(bar_rfull + 8 * s, 1);                      // the TMA issuer's arrive.expect_tx
-                mbar_init(bar_rempty + 8 * s, TC_PRODUCER_WARPS);     // one arrive per producer warp
             }
             mbar_init(bar_accum, 1);
             fence_mbar_init();
@@ -368,67 +340,92 @@ rsvd_apply_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
 
     if (warp < TC_PRODUCER_WARPS) {
         // =============================== producers ===============================
-        // TRANS 0: A tile = 128 cells x 64 genes, K-major.   chunk col = tid%8 (8 genes), rows tid/8 + 64 i
-        //          raw tile rows are 128 B (64 genes); constants = s_g/T of the stage's 64 genes
-        // TRANS 1: A tile = 128 genes x 64 cells, MN-major.  chunk col = tid%16 (8 genes), cells tid/16 + 32 i
-        //          raw tile rows are 256 B (128 genes); constants = r_c of the stage's 64 cells
-        // No bounds predicates: the TMA zero-fills counts outside the matrix, rpad/tpad are 1 there (finite residuals),
-        // out-of-range k meets zero rows of Qh/Ql and out-of-range output rows are never stored.
-        const int a_col = TRANS == 0 ? (tid & 7) : (tid & 15);
-        const int a_row0 = TRANS == 0 ? (tid >> 3) : (tid >> 4);
-        constexpr int A_ROW_STEP = TRANS == 0 ? 64 : 32;
-        // shared-memory chunk offsets are affine in i (row + 64 i / + 32 i keeps row & 7): base + immediate
-        constexpr uint32_t A_OFF_STEP = TRANS == 0 ? 8192u : 4096u;
+        // group = warp / 4 owns stages it = group, group + 4, ...; tg = thread index inside the group (0..127)
+        // TRANS 0: A tile = 128 cells x 64 genes, K-major.   chunk col = tg%8  (8 genes), rows  tg/8  + 16 j, j < 8
+        // TRANS 1: A tile = 128 genes x 64 cells, MN-major.  chunk col = tg%16 (8 genes), cells tg/16 +  8 j, j < 8
+        // No bounds predicates: row / cell indices are clamped to the matrix (their products meet zero panel rows or are
+        // never stored), columns are clamped to ld - 8, rpad / tpad are 1 beyond the matrix so every residual is finite.
+        const int group = warp / TC_GROUP_WARPS, tg = tid & (TC_GROUP_WARPS * 32 - 1);
+        const int a_col = TRANS == 0 ? (tg & 7) : (tg & 15);
+        const int a_row0 = TRANS == 0 ? (tg >> 3) : (tg >> 4);
+        constexpr int A_ROW_STEP = TRANS == 0 ? 16 : 8;
+        // shared-memory chunk offsets are affine in j (row + 16 j / cell + 8 j keeps row & 7): base + immediate
+        constexpr uint32_t A_OFF_STEP = TRANS == 0 ? 2048u : 1024u;
         const uint32_t a_off0 = TRANS == 0 ? swz128(a_row0, a_col)
                                            : (uint32_t)(a_col >> 3) * 8192u + swz128(a_row0, a_col & 7);
-        constexpr uint32_t RAW_ROW_BYTES = TRANS == 0 ? 128u : 256u;
-        const uint32_t raw_off0 = (uint32_t)a_row0 * RAW_ROW_BYTES + (uint32_t)a_col * 16u;
-        const uint32_t cst_off0 = TC_RAW_TILE_BYTES + (TRANS == 0 ? (uint32_t)a_col * 16u : (uint32_t)a_row0 * 4u);
+        const int32_t c_last = (int32_t)(a.C - 1);
+        const int64_t ld = a.ld;
 
-        float fix[8];                  // TRANS 0: r of the 2 cells (fix[0..1]); TRANS 1: t of the 8 genes
+        float fix[8];                  // TRANS 0: r of the 8 cells; TRANS 1: t of the 8 genes
+        const uint16_t *col_base;      // TRANS 1: counts + first gene of this thread's chunk
         if (TRANS == 0) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) fix[i] = __ldg(a.rpad + m0 + a_row0 + A_ROW_STEP * i);   // rpad covers ceil128(C)
+            for (int j = 0; j < TC_CHUNKS; ++j) fix[j] = __ldg(a.rpad + m0 + a_row0 + A_ROW_STEP * j);   // rpad covers ceil128(C)
+            col_base = a.counts;
         } else {
-            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.tpad + m0 + a_col * 8));    // tpad covers ceil128(ld)
-            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.tpad + m0 + a_col * 8) + 1);
+            const int64_t g_fixed = min(m0 + a_col * 8, ld - 8);
+            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.tpad + g_fixed));
+            const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.tpad + g_fixed) + 1);
             fix[0] = t0.x; fix[1] = t0.y; fix[2] = t0.z; fix[3] = t0.w;
             fix[4] = t1.x; fix[5] = t1.y; fix[6] = t1.z; fix[7] = t1.w;
+            col_base = a.counts + g_fixed;
         }
 
-        for (int it = 0; it < n_it; ++it) {
-            const int s = it % TC_STAGES, rs = it % TC_RAW_STAGES;
-            const uint32_t ph = (it / TC_STAGES) & 1, rph = (it / TC_RAW_STAGES) & 1;
-            const uint32_t rb = raw_base + rs * TC_RAW_BYTES;
-            mbar_wait_backoff(bar_rfull + 8 * rs, rph);       // raw counts + constants have landed
-            uint4 raw[2];
-            float cst[TRANS == 0 ? 8 : 2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) raw[i] = lds128(rb + raw_off0 + A_ROW_STEP * RAW_ROW_BYTES * i);
+        uint4 raw[TC_CHUNKS];
+        float cst[8];                  // TRANS 0: t of the stage's 8 genes of this thread; TRANS 1: r of its 8 cells
+        auto load_chunk = [&](int it, int j) {
+            const int64_t kk = k_lo + (int64_t)it * TC_TK;
             if constexpr (TRANS == 0) {
-                const uint4 c0 = lds128(rb + cst_off0), c1 = lds128(rb + cst_off0 + 128);   // permuted block: conflict-free
-                cst[0] = __uint_as_float(c0.x); cst[1] = __uint_as_float(c0.y); cst[2] = __uint_as_float(c0.z);
-                cst[3] = __uint_as_float(c0.w); cst[4] = __uint_as_float(c1.x); cst[5] = __uint_as_float(c1.y);
-                cst[6] = __uint_as_float(c1.z); cst[7] = __uint_as_float(c1.w);
+                const int32_t row = min((int32_t)(m0 + a_row0 + A_ROW_STEP * j), c_last);
+                const int64_t g0 = min(kk + a_col * 8, ld - 8);
+                raw[j] = __ldg(reinterpret_cast<const uint4 *>(col_base + (int64_t)row * ld + g0));
+            } else {
+                const int32_t row = min((int32_t)(kk + a_row0 + A_ROW_STEP * j), c_last);
+                raw[j] = __ldg(reinterpret_cast<const uint4 *>(col_base + (int64_t)row * ld));
+            }
+        };
+        auto load_cst = [&](int it) {
+            const int64_t kk = k_lo + (int64_t)it * TC_TK;
+            if constexpr (TRANS == 0) {
+                const int64_t g0 = min(kk + a_col * 8, ld - 8);
+                const float4 t0 = __ldg(reinterpret_cast<const float4 *>(a.tpad + g0));
+                const float4 t1 = __ldg(reinterpret_cast<const float4 *>(a.tpad + g0) + 1);
+                cst[0] = t0.x; cst[1] = t0.y; cst[2] = t0.z; cst[3] = t0.w;
+                cst[4] = t1.x; cst[5] = t1.y; cst[6] = t1.z; cst[7] = t1.w;
             } else {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) cst[i] = lds32f(rb + cst_off0 + A_ROW_STEP * 4 * i);
+                for (int j = 0; j < TC_CHUNKS; ++j) cst[j] = __ldg(a.rpad + kk + a_row0 + A_ROW_STEP * j);   // rpad covers ceil64(C)
             }
-            uint4 hi[2], lo[2];                               // the math first, the wait for a free UMMA stage after it
+        };
+
+        if (group < n_it) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                if constexpr (TRANS == 0) resid8<LO_CLIP, true>(raw[i], cst, fix[i], a.inv_theta, a.clip, a.magic, hi[i], lo[i]);
-                else resid8<LO_CLIP, false>(raw[i], fix, cst[i], a.inv_theta, a.clip, a.magic, hi[i], lo[i]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);  // this warp is done reading the raw stage
-            mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1);     // UMMA stage free (passes at once on the first lap)
+            for (int j = 0; j < TC_CHUNKS; ++j) load_chunk(group, j);
+            load_cst(group);
+        }
+        for (int it = group; it < n_it; it += TC_GROUPS) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1;
             const uint32_t st = smem_base + s * TC_STAGE_BYTES + a_off0;
+            const bool more = it + TC_GROUPS < n_it;
+            uint4 hi, lo;
+            // chunk 0 is computed before the wait for the UMMA slot: the slot was last used by this group's own previous
+            // stage, whose MMAs were issued a few hundred cycles ago
+            if constexpr (TRANS == 0) resid8<LO_CLIP, true>(raw[0], cst, fix[0], a.inv_theta, a.clip, a.magic, hi, lo);
+            else resid8<LO_CLIP, false>(raw[0], fix, cst[0], a.inv_theta, a.clip, a.magic, hi, lo);
+            if (more) load_chunk(it + TC_GROUPS, 0);
+            mbar_wait_backoff(bar_empty + 8 * s, ph ^ 1);     // passes at once on the first lap
+            sts128(st, hi);
+            sts128(st + TC_A_BYTES, lo);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                sts128(st + A_OFF_STEP * i, hi[i]);
-                sts128(st + TC_A_BYTES + A_OFF_STEP * i, lo[i]);
+            for (int j = 1; j < TC_CHUNKS; ++j) {
+                if constexpr (TRANS == 0) resid8<LO_CLIP, true>(raw[j], cst, fix[j], a.inv_theta, a.clip, a.magic, hi, lo);
+                else resid8<LO_CLIP, false>(raw[j], fix, cst[j], a.inv_theta, a.clip, a.magic, hi, lo);
+                if (more) load_chunk(it + TC_GROUPS, j);      // the register of the chunk just consumed takes the next one
+                sts128(st + A_OFF_STEP * j, hi);
+                sts128(st + TC_A_BYTES + A_OFF_STEP * j, lo);
             }
+            if (more) load_cst(it + TC_GROUPS);
             fence_proxy_async_smem();                         // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -507,7 +504,7 @@ rsvd_apply_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
             if (n_it > 0) umma_commit_elect(bar_accum);       // accumulator complete
         }
         __syncwarp();
-    } else if (warp == TC_PRODUCER_WARPS + 1) {
+    } else {
         // =============================== panel-tile copy issuer (one thread) ===============================
         if (lane == 0) {
             const char *qh = reinterpret_cast<const char *>(a.Qh) + (k_lo / TC_TK) * TC_B_BYTES;
@@ -520,23 +517,6 @@ rsvd_apply_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
                 mbar_arrive_expect_tx(bar_full + 8 * s, 2 * TC_B_BYTES);
                 bulk_g2s(b_hi, qh + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_full + 8 * s);
                 bulk_g2s(b_hi + TC_B_BYTES, ql + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_full + 8 * s);
-            }
-        }
-        __syncwarp();
-    } else {
-        // =============================== raw count tile TMA issuer (one thread) ===============================
-        if (lane == 0) {
-            const float *cst_src = (TRANS == 0 ? a.tperm : a.rpad) + k_lo;       // 64 floats per stage
-            for (int it = 0; it < n_it; ++it) {
-                const int rs = it % TC_RAW_STAGES;
-                const uint32_t rph = (it / TC_RAW_STAGES) & 1;
-                mbar_wait_backoff(bar_rempty + 8 * rs, rph ^ 1);
-                const uint32_t rb = raw_base + rs * TC_RAW_BYTES;
-                const int32_t kk = (int32_t)(k_lo + (int64_t)it * TC_TK);
-                mbar_arrive_expect_tx(bar_rfull + 8 * rs, TC_RAW_BYTES);
-                if (TRANS == 0) tma_load_2d(rb, &tmap, kk, (int32_t)m0, bar_rfull + 8 * rs);      // {gene, cell}
-                else tma_load_2d(rb, &tmap, (int32_t)m0, kk, bar_rfull + 8 * rs);
-                bulk_g2s(rb + TC_RAW_TILE_BYTES, cst_src + (int64_t)it * TC_TK, TC_TK * 4, bar_rfull + 8 * rs);
             }
         }
         __syncwarp();
@@ -591,37 +571,8 @@ static int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 static int64_t ceil64(int64_t x) { return (x + 63) / 64 * 64; }
 static int64_t ceil128(int64_t x) { return (x + 127) / 128 * 128; }
 
-// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
-static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-    }();
-    return fn;
-}
-
-// 2-D tensor map over the uint16 count matrix (C rows x G columns, row pitch ld): box = box_cols x box_rows
-static int make_counts_tmap(CUtensorMap *tm, const uint16_t *counts, int64_t C, int64_t G, int64_t ld, uint32_t box_cols,
-                            uint32_t box_rows) {
-    auto enc = tensor_map_encoder();
-    if (!enc) return gc::fail("gc_rsvd_apply", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
-    const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)C};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(counts), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return gc::fail("cuTensorMapEncodeTiled", "failed to encode the count-matrix tensor map");
-    return 0;
-}
-
 struct TcScratch {
-    float *partials; __nv_bfloat16 *Qh, *Ql; double *colsum_part; float *colsum, *rpad, *tpad, *tperm;
+    float *partials; __nv_bfloat16 *Qh, *Ql; double *colsum_part; float *colsum, *rpad, *tpad;
     int n_split; int64_t k_per_split; int prep_blocks; int64_t bytes;
 };
 
@@ -640,7 +591,6 @@ static TcScratch tc_layout(char *base, int64_t C, int64_t ld, int64_t n_out, int
     s.colsum = (float *)p;               p += 512;
     s.rpad = (float *)p;                 p += align256(ceil128(C) * 4);
     s.tpad = (float *)p;                 p += align256(ceil128(ld) * 4);
-    s.tperm = (float *)p;                p += align256(ceil128(ld) * 4);
     s.bytes = p - base;
     return s;
 }
@@ -654,14 +604,14 @@ extern "C" int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G) {
 }
 
 template <int TRANS, bool LO_CLIP>
-static int tc_launch(const TcArgs &a, const CUtensorMap &tmap, dim3 grid, cudaStream_t st) {
+static int tc_launch(const TcArgs &a, dim3 grid, cudaStream_t st) {
     static thread_local bool configured = false;
     if (!configured) {
         GC_CUDA(cudaFuncSetAttribute(rsvd_apply_tc_kernel<TRANS, LO_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_BYTES));
         configured = true;
     }
-    rsvd_apply_tc_kernel<TRANS, LO_CLIP><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a, tmap);
+    rsvd_apply_tc_kernel<TRANS, LO_CLIP><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
     return 0;
 }
 
@@ -683,7 +633,7 @@ extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float
     a.n_k = trans == 0 ? M->G : M->C;
     const TcScratch s = tc_layout((char *)scratch, M->C, M->ld, a.n_out, a.n_k);
     a.n_split = s.n_split; a.k_per_split = s.k_per_split;
-    a.partials = s.partials; a.Qh = s.Qh; a.Ql = s.Ql; a.rpad = s.rpad; a.tpad = s.tpad; a.tperm = s.tperm;
+    a.partials = s.partials; a.Qh = s.Qh; a.Ql = s.Ql; a.rpad = s.rpad; a.tpad = s.tpad;
     const int64_t n_tiles = ceil_div<int64_t>(a.n_out, TC_TM);
     // centring: M = Z - row_shift[c] - col_shift[g]; the shift indexed by k goes into colsum[64..], the one indexed by
     // the output row multiplies colsum[0..63]
@@ -692,23 +642,19 @@ extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float
 
     tc_prep_kernel<<<s.prep_blocks, 256, 0, st>>>(Qin, a.n_k, ceil64(a.n_k), k_shift, s.Qh, s.Ql, s.colsum_part,
                                                   M->row_sum_f, M->C, ceil128(M->C), M->col_sum_f, M->G, ceil128(M->ld),
-                                                  1.0f / M->total, s.rpad, s.tpad, s.tperm);
+                                                  1.0f / M->total, s.rpad, s.tpad);
     if (int rc = check_launch("tc_prep_kernel")) return rc;
     tc_colsum_kernel<<<1, 128, 0, st>>>(s.colsum_part, s.prep_blocks, s.colsum);
     if (int rc = check_launch("tc_colsum_kernel")) return rc;
 
     GC_REQUIRE(a.n_split <= 65535, "too many k slabs");
-    GC_REQUIRE(M->C < (1ll << 31) && M->ld < (1ll << 31), "matrix dimensions must fit in int32 (TMA coordinates)");
-    CUtensorMap tmap;
-    if (int rc = trans == 0 ? make_counts_tmap(&tmap, M->counts, M->C, M->G, M->ld, TC_TK, TC_TM)
-                            : make_counts_tmap(&tmap, M->counts, M->C, M->G, M->ld, TC_TM, TC_TK))
-        return rc;
+    GC_REQUIRE(M->C < (1ll << 31), "more than 2^31 cells");
     dim3 grid((unsigned)n_tiles, (unsigned)a.n_split);
     const bool lo_clip = !(M->clip * M->clip >= M->theta);     // z > -sqrt(theta) always: lower clip is dead otherwise
     prof_begin(kProfRsvdPass, st);
     int rc;
-    if (trans == 0) rc = lo_clip ? tc_launch<0, true>(a, tmap, grid, st) : tc_launch<0, false>(a, tmap, grid, st);
-    else rc = lo_clip ? tc_launch<1, true>(a, tmap, grid, st) : tc_launch<1, false>(a, tmap, grid, st);
+    if (trans == 0) rc = lo_clip ? tc_launch<0, true>(a, grid, st) : tc_launch<0, false>(a, grid, st);
+    else rc = lo_clip ? tc_launch<1, true>(a, grid, st) : tc_launch<1, false>(a, grid, st);
     prof_end(kProfRsvdPass, st);
     if (rc) return rc;
     if (int rc2 = check_launch("rsvd_apply_tc_kernel")) return rc2;
