@@ -35,18 +35,149 @@ def _residual_columns(adata, mask: np.ndarray) -> np.ndarray:
     return np.asarray(adata.X)[:, mask]
 
 
+_RAND_R_MAX = 2147483647
+_EULER_GAMMA = float(np.euler_gamma)
+
+
+def _avg_path_length(n: int) -> float:
+    """`_average_path_length` of sklearn ensemble/_iforest.py:647-681 for one leaf size."""
+    if n <= 1:
+        return 0.0
+    if n == 2:
+        return 1.0
+    return float(2.0 * (np.log(n - 1.0) + _EULER_GAMMA) - 2.0 * (n - 1.0) / n)
+
+
+def _first_randint31(seeds: np.ndarray) -> np.ndarray:
+    """`[RandomState(s).randint(2**31 - 1) for s in seeds]` (equally `.randint(0, 2**31 - 1)`), vectorised over the
+    seeds: MT19937 `init_genrand(s)`, the first regenerated word (needs init words 0, 1 and 397 only), tempering,
+    then numpy's masked rejection for a 31-bit range (keep `word & 0x7fffffff` unless it equals 2**31 - 1 - the one
+    value in 2**31 that needs a second word; those seeds go through RandomState itself)."""
+    seeds = np.asarray(seeds, dtype=np.uint64)
+    mt_prev = seeds & np.uint64(0xFFFFFFFF)
+    mt0 = mt_prev.copy()
+    mt1 = mt397 = None
+    for i in range(1, 398):
+        mt_prev = (np.uint64(1812433253) * (mt_prev ^ (mt_prev >> np.uint64(30))) + np.uint64(i)) & np.uint64(0xFFFFFFFF)
+        if i == 1:
+            mt1 = mt_prev
+        if i == 397:
+            mt397 = mt_prev
+    yv = (mt0 & np.uint64(0x80000000)) | (mt1 & np.uint64(0x7FFFFFFF))
+    word = mt397 ^ (yv >> np.uint64(1)) ^ np.where(yv & np.uint64(1), np.uint64(0x9908B0DF), np.uint64(0))
+    word ^= word >> np.uint64(11)
+    word ^= (word << np.uint64(7)) & np.uint64(0x9D2C5680)
+    word ^= (word << np.uint64(15)) & np.uint64(0xEFC60000)
+    word ^= word >> np.uint64(18)
+    out = (word & np.uint64(0x7FFFFFFF)).astype(np.int64)
+    for k in np.flatnonzero(out == 0x7FFFFFFF):                       # rejected draw (probability 2**-31)
+        out[k] = np.random.RandomState(int(seeds[k])).randint(np.iinfo(np.int32).max)
+    return out
+
+
+def _isolation_forest_1d(values: np.ndarray, random_state: int, n_estimators: int = 100,
+                         return_scores: bool = False) -> np.ndarray:
+    """`IsolationForest(random_state=seed).fit_predict(values.reshape(-1, 1)) == -1` for at most 256 finite values,
+    restated from scikit-learn 1.9.0 so that the ~0.7 ms of Python overhead sklearn spends per tree (clone, parameter
+    validation, 100 estimator objects) is not paid for a handful of scalars:
+
+    * ensemble/_bagging.py:398-520: seeds = RandomState(seed).randint(2**31 - 1, size=100); tree i gets
+      random_state = RandomState(seeds[i]).randint(2**31 - 1) (ensemble/_base.py:49-99); with max_samples =
+      min(256, n) = n and bootstrap=False every tree sees every sample (unit weights);
+    * tree/_splitter.pyx Splitter.__cinit__: rand_r state = RandomState(tree seed).randint(0, 2**31 - 1);
+    * tree/_tree.pyx:140-330 depth-first build, left child first, max_depth = ceil(log2(max(n, 2))); a node with >= 2
+      samples, depth < max_depth and impure y draws (tree/_splitter.pyx:507-700, one feature): rand_int(0, 1) [one
+      xorshift step, utils/_random.pxd:20-34], then, unless max <= min + 1e-7 in float32, threshold =
+      (max - min) * rand / 2147483647 + min in float64 (tree/_utils.pyx:57-61), reset to min when it equals max;
+      samples with value <= threshold go left;
+    * ensemble/_iforest.py:529-640: depth of a sample in a tree = node depth + c(leaf size); score =
+      -2 ** (-sum(depths) / (100 c(n))); outlier iff score - (-0.5) < 0.
+
+    The regression target y = RandomState(seed).uniform(size=n) (ensemble/_iforest.py:350) only enters through the
+    "impurity <= eps" leaf test, which is evaluated here with the plain variance formula.
+    Checked against sklearn itself (flags and score_samples) on random inputs in tests/test_host_logic.py."""
+    x32 = np.asarray(values, dtype=np.float64).astype(np.float32)
+    n = x32.shape[0]
+    xs = [float(v) for v in x32]                      # float32 values as Python floats (exact)
+    ys = np.random.RandomState(random_state).uniform(size=n).tolist()
+    max_depth = int(np.ceil(np.log2(max(n, 2))))
+    seeds = np.random.RandomState(random_state).randint(np.iinfo(np.int32).max, size=n_estimators)
+    states = _first_randint31(_first_randint31(seeds)).tolist()
+    eps = float(np.finfo(np.float64).eps)
+    c_of = [_avg_path_length(m) for m in range(n + 1)]
+    depths = [0.0] * n
+    for state in states:
+        contrib = [0.0] * n
+        stack = [(list(range(n)), 0)]                 # (sample ids, depth); left child is pushed last = built first
+        while stack:
+            ids, depth = stack.pop()
+            m = len(ids)
+            leaf = depth >= max_depth or m < 2
+            if not leaf:
+                s1 = s2 = 0.0
+                for i in ids:
+                    s1 += ys[i]
+                    s2 += ys[i] * ys[i]
+                leaf = s2 / m - (s1 / m) ** 2 <= eps
+            if not leaf:
+                # rand_int(0, 1): the (only) feature is drawn - one xorshift step of our_rand_r
+                if state == 0:
+                    state = 1
+                state ^= (state << 13) & 0xFFFFFFFF
+                state ^= state >> 17
+                state ^= (state << 5) & 0xFFFFFFFF
+                lo = hi = xs[ids[0]]
+                for i in ids:
+                    v = xs[i]
+                    if v < lo:
+                        lo = v
+                    elif v > hi:
+                        hi = v
+                if hi - lo < 1e-6 and np.float32(hi) <= np.float32(lo) + np.float32(1e-7):
+                    leaf = True                       # constant feature (float32 test of the splitter): no split
+                else:
+                    if state == 0:
+                        state = 1
+                    state ^= (state << 13) & 0xFFFFFFFF
+                    state ^= state >> 17
+                    state ^= (state << 5) & 0xFFFFFFFF
+                    thr = (hi - lo) * float(state & 0x7FFFFFFF) / 2147483647.0 + lo
+                    if thr == hi:
+                        thr = lo
+                    left, right = [], []
+                    for i in ids:
+                        (left if xs[i] <= thr else right).append(i)
+                    stack.append((right, depth + 1))
+                    stack.append((left, depth + 1))
+            if leaf:
+                d = (depth + 1) + c_of[m] - 1.0
+                for i in ids:
+                    contrib[i] = d
+        for i in range(n):
+            depths[i] += contrib[i]
+    depths = np.asarray(depths)
+    denominator = n_estimators * c_of[n]
+    scores = -(2 ** (-np.divide(depths, denominator, out=np.ones_like(depths), where=denominator != 0)))
+    if return_scores:
+        return scores
+    return scores - (-0.5) < 0
+
+
 def _isolation_forest_outliers(values: np.ndarray, random_state: int) -> np.ndarray:
     """`IsolationForest(random_state=...).fit_predict(values.reshape(-1, 1)) == -1` (scGeneClust/tl/selection.py:51).
 
-    With one or two samples the forest's answer does not depend on its random draws, so it is written down instead
-    of fitting 100 trees (~0.1 s of Python overhead): max_samples_ = n, so every tree holds all samples; for n = 1
-    the normaliser c(1) = 0 makes every score exactly -0.5, for n = 2 every tree isolates both samples at depth 1
-    (or keeps two equal values in one leaf, path length c(2) = 1) and every score is -2^(-1) = -0.5 as well.
-    `offset_` is -0.5 (contamination='auto'), the decision function is 0 and `predict` flags only values < 0:
-    no outlier.  (sklearn 1.9.0 ensemble/_iforest.py:297-380, :529-640.)  Non-finite input other than NaN makes
-    sklearn raise, so that case - and every n >= 3 - still goes through sklearn itself."""
-    if values.shape[0] <= 2 and not np.isinf(values).any():
-        return np.zeros(values.shape[0], dtype=bool)
+    With one or two samples the forest's answer does not depend on its random draws: max_samples_ = n, so every tree
+    holds all samples; for n = 1 the normaliser c(1) = 0 makes every score exactly -0.5, for n = 2 every tree isolates
+    both samples at depth 1 (or keeps two equal values in one leaf, path length c(2) = 1) and every score is
+    -2^(-1) = -0.5 as well; `offset_` is -0.5, the decision function is 0 and `predict` flags only values < 0: no
+    outlier.  Up to 64 finite values use the line-by-line restatement above; anything else (more values, NaN / inf,
+    which make sklearn take its missing-value path or raise) goes through sklearn itself."""
+    n = values.shape[0]
+    finite = bool(np.isfinite(values).all())
+    if n <= 2 and not np.isinf(values).any():
+        return np.zeros(n, dtype=bool)
+    if n <= 64 and finite and bool(np.isfinite(values.astype(np.float32)).all()):
+        return _isolation_forest_1d(values, random_state)
     return IsolationForest(random_state=random_state).fit_predict(values.reshape(-1, 1)) == -1
 
 

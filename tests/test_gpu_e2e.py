@@ -113,3 +113,38 @@ def test_ps_stages_vs_oracle(torch_cuda, data):
     sample = edges[:: max(1, len(edges) // 12)]
     ref_c = stages.gene_complementarity(ad.X, labels, sample, 0)
     assert np.array_equal(ad.uns['mst_edges_complm'][:: max(1, len(edges) // 12)], ref_c)
+
+
+def test_ps_entry_point_end_to_end(torch_cuda, data):
+    """`scGeneClust(adata, version='ps', n_obs_clusters=8, return_info=True)` with the pseudo cell types supplied in
+    `obs['cluster']`: every slot of the reference's out-contract is filled (scGeneClust/_model.py:86-99), the redundancy
+    matrix is exactly symmetric (the reference's own test, tests/test_GeneClust.py:22-23), the MST spans the relevant
+    genes, and the HDBSCAN tail agrees with scikit-learn's fork run on the same MST."""
+    from sklearn.cluster._hdbscan import _linkage, _tree
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    X, names, types = data
+    X, names = X[:1500, :700], names[:700]
+    ok = (X > 0).sum(0) >= 3
+    X, names = np.ascontiguousarray(X[:, ok]), names[ok]
+    raw = AnnDataLite(X.astype(np.float32), var_names=names)
+    raw.obs['cluster'] = np.array([f"type{t}" for t in types[:1500]])
+    info, genes = scGeneClust(raw, version='ps', n_obs_clusters=8, return_info=True, verbosity=0)
+    assert genes.shape[0] > 0 and set(genes) <= set(names)                   # reference test: genes.shape[0] > 0
+    n = info.n_vars
+    R = info.varp['redundancy']
+    assert R.shape == (n, n) and np.array_equal(R, R.T) and not np.diag(R).any()
+    assert info.uns['mst_edges'].shape == (n - 1, 2) and info.uns['mst_edges_complm'].shape == (n - 1,)
+    for col in ('relevance', 'outlier_score', 'cluster', 'representative'):
+        assert col in info.var
+    assert np.array_equal(np.asarray(info.var_names)[info.var['representative'].to_numpy()], genes)
+    # the tail: rebuild the scaled MST exactly as scGeneClust/tl/cluster.py:122-126 does and hand it to sklearn's fork
+    e = info.uns['mst_edges']
+    rel = info.var['relevance'].to_numpy()
+    scale = np.maximum(np.minimum(rel[e[:, 0]], rel[e[:, 1]]), info.uns['mst_edges_complm']) / R[e[:, 0], e[:, 1]]
+    order = np.argsort(scale)
+    rec = np.zeros(n - 1, dtype=_linkage.MST_edge_dtype)
+    rec['current_node'], rec['next_node'], rec['distance'] = e[order, 0], e[order, 1], scale[order]
+    ref_labels, _ = _tree.tree_to_labels(_linkage.make_single_linkage(rec), 3, "eom", False, 0.0, None)
+    assert np.array_equal(info.var['cluster'].to_numpy(), ref_labels)
+    s = info.var['outlier_score'].to_numpy()
+    assert (s >= 0).all() and (s <= 1).all()

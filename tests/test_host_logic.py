@@ -129,3 +129,64 @@ def test_minibatch_sampling_restatement_equals_randomstate_choice():
         assert a.randint(1 << 30) == b.randint(1 << 30)          # both streams consumed the same amount
     a, b = np.random.RandomState(5), np.random.RandomState(5)
     assert np.array_equal(np.stack([a.uniform(size=7) for _ in range(9)]), b.uniform(size=(9, 7)))
+
+
+def test_isolation_forest_restatement_equals_sklearn():
+    """The singleton-rescue outlier test (scGeneClust/tl/selection.py:51) runs a line-by-line restatement of sklearn's
+    1-D IsolationForest; its score_samples must be bit-identical to sklearn's own, incl. ties / near-constant data."""
+    import numpy as np
+    from sklearn.ensemble import IsolationForest
+    from scgeneclust_b200.tl.selection import _first_randint31, _isolation_forest_1d, _isolation_forest_outliers
+    sd = np.array([0, 1, 5, 123456, 2 ** 31 - 2, 99999999])
+    assert np.array_equal(_first_randint31(sd), [np.random.RandomState(int(s)).randint(2 ** 31 - 1) for s in sd])
+    rs = np.random.RandomState(2)
+    for trial in range(25):
+        n, seed = int(rs.randint(3, 64)), int(rs.randint(0, 1000))
+        kind = trial % 5
+        if kind == 0:
+            v = rs.normal(size=n) * 1e4
+        elif kind == 1:
+            v = np.round(rs.normal(size=n), 1) * 100                         # ties
+        elif kind == 2:
+            v = rs.lognormal(size=n) * 1e5
+        elif kind == 3:
+            v = np.concatenate([rs.normal(size=n - 1), [50.0]])              # one obvious outlier
+        else:
+            v = np.concatenate([np.full(n - 2, 3.25), rs.normal(size=2) * 1e-8 + 3.25])   # constant in float32
+        forest = IsolationForest(random_state=seed).fit(v.reshape(-1, 1))
+        assert np.array_equal(_isolation_forest_1d(v, seed, return_scores=True), forest.score_samples(v.reshape(-1, 1)))
+        assert np.array_equal(_isolation_forest_outliers(v, seed), forest.predict(v.reshape(-1, 1)) == -1)
+    for n in (1, 2):                                                         # closed-form small cases
+        v = rs.normal(size=n)
+        assert np.array_equal(_isolation_forest_outliers(v, 0),
+                              IsolationForest(random_state=0).fit_predict(v.reshape(-1, 1)) == -1)
+
+
+def test_hdbscan_tail_labels_equal_sklearn_fork():
+    """MST -> single linkage -> condensed tree (min cluster size 3) -> EOM labels: the restatement of hdbscan's
+    functions (scGeneClust/tl/cluster.py:127-131) must agree with scikit-learn's fork of the same code
+    (`_hdbscan._linkage.make_single_linkage`, `_hdbscan._tree.tree_to_labels`); GLOSH scores are in [0, 1]."""
+    import numpy as np
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    from sklearn.cluster._hdbscan import _linkage, _tree
+    from scgeneclust_b200.tl._hdbscan_tail import mst_to_clusters, single_linkage_label
+    rs = np.random.RandomState(0)
+    for trial in range(4):
+        n = [40, 120, 300, 77][trial]
+        centers = rs.normal(size=(5, 3)) * 6
+        pts = centers[rs.randint(0, 5, n)] + rs.normal(size=(n, 3))
+        dmat = np.linalg.norm(pts[:, None] - pts[None], axis=2)
+        mst = minimum_spanning_tree(dmat).tocoo()
+        edges = np.stack([mst.row, mst.col, mst.data], axis=1)
+        edges = edges[np.argsort(edges[:, 2])]
+        labels, scores = mst_to_clusters(edges, n, min_cluster_size=3)
+        rec = np.zeros(n - 1, dtype=_linkage.MST_edge_dtype)
+        rec['current_node'], rec['next_node'], rec['distance'] = edges[:, 0].astype(np.intp), edges[:, 1].astype(np.intp), edges[:, 2]
+        slt = _linkage.make_single_linkage(rec)
+        ref_labels, _ = _tree.tree_to_labels(slt, 3, "eom", False, 0.0, None)
+        mine = single_linkage_label(edges)
+        assert np.array_equal(mine[:, 2], slt['value']) and np.array_equal(mine[:, 3], slt['cluster_size'])
+        assert np.array_equal(labels, ref_labels)
+        assert scores.shape == (n,) and (scores >= 0).all() and (scores <= 1).all()
+    with __import__('pytest').raises(ValueError):
+        mst_to_clusters(edges[:-1], n)                                        # spanning forest: the reference fails too
