@@ -36,8 +36,8 @@ class AnnDataLite:
         self._X = X
         n_obs, n_vars = X.shape
         if obs is None:
-            # default names are '0', '1', ... like anndata; they are materialised on first use of `obs_names` /
-            # `var_names` (building 10^5..10^6 strings up front would cost more than the whole device pipeline)
+            # default names ('cell_0', ... / 'gene_0', ...) are materialised on first use of `obs_names` / `var_names`
+            # (building 10^5..10^6 strings up front would cost more than the whole device pipeline)
             index = pd.Index(np.asarray(obs_names, dtype=object)) if obs_names is not None else pd.RangeIndex(n_obs)
             obs = pd.DataFrame(index=index)
         if var is None:
@@ -73,18 +73,18 @@ class AnnDataLite:
         return self._X.shape
 
     @staticmethod
-    def _named(frame: pd.DataFrame) -> pd.Index:
+    def _named(frame: pd.DataFrame, prefix: str) -> pd.Index:
         if isinstance(frame.index, pd.RangeIndex):
-            frame.index = pd.Index(np.arange(len(frame)).astype(str).astype(object))
+            frame.index = pd.Index(np.char.add(prefix, np.arange(len(frame)).astype(str)).astype(object))
         return frame.index
 
     @property
     def obs_names(self) -> pd.Index:
-        return self._named(self.obs)
+        return self._named(self.obs, "cell_")
 
     @property
     def var_names(self) -> pd.Index:
-        return self._named(self.var)
+        return self._named(self.var, "gene_")
 
     # -- copy / subset --------------------------------------------------------------------------------------
     def copy(self) -> "AnnDataLite":
