@@ -278,10 +278,19 @@ def run_native(args, rank: int, world: int, local_rank: int):
     pass_bytes = cells * (g_hi - g_lo) * 2                   # algorithmic: 2 B per matrix entry per pass
     avg_ms = tot.value / max(cnt.value, 1)
     achieved = pass_bytes / (avg_ms * 1e-3) / 1e9 if cnt.value else None
-    roofline = {"kernel": "rsvd_apply (one Y = M Q / M^T Q pass over the implicit Pearson-residual matrix)",
+    # DRAM traffic of the same kernel from the committed ncu capture (only valid for the workload it was taken on)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_rsvd_tc_v3_traffic.json")))
+        if tj["workload"] == {"cells": cells, "genes": G, "n_gpus": world}:
+            traffic = tj["mean_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"kernel": "rsvd_apply_tc_kernel (one Y = M Q / M^T Q pass over the implicit Pearson-residual matrix)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "unit": "GB/s", "frac": (achieved / peak_gbs) if achieved else None, "traffic": None,
+                "unit": "GB/s", "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic,
+                "traffic_source": "profiles/r1_rsvd_tc_v3_traffic.json (ncu dram read+write bytes per launch)" if traffic else None,
                 "launches": int(cnt.value), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": pass_bytes,
                 "share_of_step": (tot.value / args.steps) / ms_per_step if ms_per_step else None}
 
