@@ -278,7 +278,7 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t
     __shared__ float sc[kDMax];
     __shared__ double sxx;
     __shared__ double red[kKppThreads];
-    __shared__ __align__(16) float buf[kRoundChunk];
+    __shared__ __align__(16) float buf[kRoundChunk + 32];    // + zero padding: the scan reads one block ahead
     __shared__ float carry;
     __shared__ int s_best, s_is_last;
     __shared__ float s_pot;
@@ -356,32 +356,55 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t
     for (int64_t c0 = 0; c0 < n; c0 += kRoundChunk) {
         const int cn = (int)min((int64_t)kRoundChunk, n - c0);
         __syncthreads();
-        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
-            const float v = __ldcg(src + c0 + i);
-            buf[i] = v;
-            closest[c0 + i] = v;
+        // adopt: closest <- trial_dist[best] for this chunk, staged in shared memory (loads issued eight at a time)
+        {
+            const int cn4 = cn >> 2;
+            const float4 *src4 = reinterpret_cast<const float4 *>(src + c0);      // n_trials * n floats, 256-B aligned base;
+            float4 *dst4 = reinterpret_cast<float4 *>(closest + c0);             // c0 is a multiple of kRoundChunk
+            float4 *b4w = reinterpret_cast<float4 *>(buf);
+            const bool vec_ok = ((reinterpret_cast<uintptr_t>(src4) | reinterpret_cast<uintptr_t>(dst4)) & 15) == 0;
+            if (vec_ok) {
+                for (int i0 = threadIdx.x; i0 < cn4; i0 += 4 * blockDim.x) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (i0 + u * blockDim.x < cn4) v[u] = __ldcg(src4 + i0 + u * blockDim.x);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u * blockDim.x < cn4) { b4w[i0 + u * blockDim.x] = v[u]; dst4[i0 + u * blockDim.x] = v[u]; }
+                }
+                for (int i = 4 * cn4 + threadIdx.x; i < cn; i += blockDim.x) {
+                    const float v = __ldcg(src + c0 + i);
+                    buf[i] = v;
+                    closest[c0 + i] = v;
+                }
+            } else {
+                for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+                    const float v = __ldcg(src + c0 + i);
+                    buf[i] = v;
+                    closest[c0 + i] = v;
+                }
+            }
+            for (int i = cn + threadIdx.x; i < ((cn + 15) & ~15) + 16; i += blockDim.x) buf[i] = 0.f;   // x + 0 = x
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            // the dependent float32 add chain of np.cumsum (4 cycles per element); the shared-memory loads of the next
-            // 16 elements are issued before the chain of the current 16 so their latency stays off the critical path
+            // the dependent float32 add chain of np.cumsum (4 cycles per element).  Blocks of 16; the shared-memory
+            // loads of the next block are issued before the chain of the current one (the zero padding makes the
+            // read-ahead of the last block harmless), so only the adds are on the critical path.
             float acc = carry;
-            int i = 0;
             float4 *b4 = reinterpret_cast<float4 *>(buf);
-            if (cn >= 16) {
-                float4 a0 = b4[0], a1 = b4[1], a2 = b4[2], a3 = b4[3];
-                for (; i + 16 <= cn; i += 16) {
-                    float4 n0 = a0, n1 = a1, n2 = a2, n3 = a3;
-                    if (i + 32 <= cn) { n0 = b4[(i >> 2) + 4]; n1 = b4[(i >> 2) + 5]; n2 = b4[(i >> 2) + 6]; n3 = b4[(i >> 2) + 7]; }
-                    acc = acc + a0.x; a0.x = acc; acc = acc + a0.y; a0.y = acc; acc = acc + a0.z; a0.z = acc; acc = acc + a0.w; a0.w = acc;
-                    acc = acc + a1.x; a1.x = acc; acc = acc + a1.y; a1.y = acc; acc = acc + a1.z; a1.z = acc; acc = acc + a1.w; a1.w = acc;
-                    acc = acc + a2.x; a2.x = acc; acc = acc + a2.y; a2.y = acc; acc = acc + a2.z; a2.z = acc; acc = acc + a2.w; a2.w = acc;
-                    acc = acc + a3.x; a3.x = acc; acc = acc + a3.y; a3.y = acc; acc = acc + a3.z; a3.z = acc; acc = acc + a3.w; a3.w = acc;
-                    b4[(i >> 2)] = a0; b4[(i >> 2) + 1] = a1; b4[(i >> 2) + 2] = a2; b4[(i >> 2) + 3] = a3;
-                    a0 = n0; a1 = n1; a2 = n2; a3 = n3;
-                }
+            const int nb = (cn + 15) >> 4;
+            float4 a0 = b4[0], a1 = b4[1], a2 = b4[2], a3 = b4[3];
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                const float4 n0 = b4[4 * b + 4], n1 = b4[4 * b + 5], n2 = b4[4 * b + 6], n3 = b4[4 * b + 7];
+                acc = acc + a0.x; a0.x = acc; acc = acc + a0.y; a0.y = acc; acc = acc + a0.z; a0.z = acc; acc = acc + a0.w; a0.w = acc;
+                acc = acc + a1.x; a1.x = acc; acc = acc + a1.y; a1.y = acc; acc = acc + a1.z; a1.z = acc; acc = acc + a1.w; a1.w = acc;
+                acc = acc + a2.x; a2.x = acc; acc = acc + a2.y; a2.y = acc; acc = acc + a2.z; a2.z = acc; acc = acc + a2.w; a2.w = acc;
+                acc = acc + a3.x; a3.x = acc; acc = acc + a3.y; a3.y = acc; acc = acc + a3.z; a3.z = acc; acc = acc + a3.w; a3.w = acc;
+                b4[4 * b] = a0; b4[4 * b + 1] = a1; b4[4 * b + 2] = a2; b4[4 * b + 3] = a3;
+                a0 = n0; a1 = n1; a2 = n2; a3 = n3;
             }
-            for (; i < cn; ++i) { acc = acc + buf[i]; buf[i] = acc; }
             carry = acc;
         }
         __syncthreads();
