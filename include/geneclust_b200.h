@@ -160,6 +160,13 @@ int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, const float *c
 int gc_closeness(const float *dist, const int32_t *labels, int64_t n, int K, int32_t *scratch, float *closeness,
                  void *stream);
 
+/* a5  Binomial deviance of the singleton-cluster genes (post-hoc filtering): compute_deviance of
+ * scGeneClust/tl/selection.py:82-89 on the float32 residual columns X (C x m, row-major, contiguous), with numpy's
+ * float32 operation and summation order (pairwise / row-after-row); out[m] float32.
+ * scratch: gc_binomial_deviance_scratch_bytes(C, m), 256-byte aligned. */
+int64_t gc_binomial_deviance_scratch_bytes(int64_t C, int m);
+int gc_binomial_deviance(const float *X, int64_t C, int m, float *out, void *scratch, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * a6/a7/a8  kNN mutual information (GeneClust-ps).  Replaces sklearn mutual_info_classif /
  * mutual_info_regression (feature_selection/_mutual_info.py:20-153, :294-315) called per gene / per pair /

@@ -23,6 +23,7 @@ SOURCES = [
     ("small_dense.cu", []),
     ("rsvd_tc.cu", []),
     ("rng_kernels.cu", ["-fmad=false"]),
+    ("deviance_kernels.cu", ["-fmad=false"]),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-I", os.path.join(ROOT, "include"), "-I", HERE]

@@ -23,6 +23,33 @@ def compute_deviance(X: np.ndarray) -> np.ndarray:
     return 2 * (left_half + right_half)
 
 
+def device_deviance(Xd) -> np.ndarray:
+    """`compute_deviance` of a device-resident float32 (cells x m) residual block, on the device
+    (gc_binomial_deviance: numpy's float32 operation and summation order); returns the host float32[m] vector."""
+    import torch
+    from .._lib import lib, ptr, stream_handle
+    L = lib()
+    Xd = Xd.contiguous()
+    C_, m = Xd.shape
+    out = torch.empty(m, dtype=torch.float32, device=Xd.device)
+    scratch = torch.empty(L.binomial_deviance_scratch_bytes(C_, m), dtype=torch.uint8, device=Xd.device)
+    L.binomial_deviance(ptr(Xd), C_, m, ptr(out), ptr(scratch), stream_handle())
+    return out.cpu().numpy()
+
+
+def _singleton_deviances(adata, mask: np.ndarray) -> np.ndarray:
+    """Deviance of the masked (singleton-cluster) genes: on the device when the residuals live there (no C x m
+    host copy, no host log pass), else the reference's numpy expression on `adata.X`."""
+    st = get_state(adata)
+    if st.Z is not None:
+        import torch
+        idx = torch.from_numpy(np.flatnonzero(mask)).to(st.Z.device)
+        return device_deviance(st.Z.index_select(1, idx))
+    if st.op is not None:
+        return device_deviance(st.op.materialize_columns(np.flatnonzero(mask)))
+    return compute_deviance(np.asarray(adata.X)[:, mask])
+
+
 def _residual_columns(adata, mask: np.ndarray) -> np.ndarray:
     """Pearson-residual columns of the masked genes as a host float32 (cells x n_masked) array."""
     st = get_state(adata)
@@ -215,7 +242,7 @@ def select_from_clusters(adata, version: Literal['fast', 'ps'], post_hoc_filteri
         is_single = np.isin(cluster, ids[counts == 1])
         if post_hoc_filtering and (n_single := int(is_single.sum())) > 0:
             single_genes = var_names[is_single]
-            deviances = compute_deviance(_residual_columns(adata, is_single))
+            deviances = _singleton_deviances(adata, is_single)
             is_outlier = _isolation_forest_outliers(deviances, random_state)
             logger.opt(colors=True).debug(
                 f"Found <yellow>{is_outlier.sum()}</yellow> outlier(s) in <yellow>{n_single}</yellow> single gene cluster(s).")

@@ -148,3 +148,22 @@ def test_ps_entry_point_end_to_end(torch_cuda, data):
     assert np.array_equal(info.var['cluster'].to_numpy(), ref_labels)
     s = info.var['outlier_score'].to_numpy()
     assert (s >= 0).all() and (s <= 1).all()
+
+
+@pytest.mark.parametrize("C,m", [(3001, 1), (3001, 2), (50000, 1), (50000, 7), (20011, 40)])
+def test_device_deviance_equals_numpy(torch_cuda, C, m):
+    """Singleton rescue: the device binomial deviance must be the reference's numpy expression
+    (scGeneClust/tl/selection.py:82-89) on float32 residual-like columns, including its NaN handling; equality up to
+    the last-bit difference between numpy's SIMD logf and CUDA's logf summed over C terms (tolerance 2e-5 relative)."""
+    torch = torch_cuda
+    from scgeneclust_b200.tl.selection import compute_deviance, device_deviance
+    rs = np.random.RandomState(C + m)
+    X = (rs.standard_normal((C, m)) * rs.uniform(0.5, 3, size=m) + rs.uniform(-0.2, 0.4, size=m)).astype(np.float32)
+    X[rs.rand(C, m) < 0.3] = np.float32(-0.31)                 # many equal negative residuals (zero counts)
+    X[rs.rand(C, m) < 0.01] = 0.0
+    ref = compute_deviance(X)
+    got = device_deviance(torch.from_numpy(X).cuda())
+    assert got.dtype == np.float32 and got.shape == (m,)
+    # left and right halves (~1e4) cancel to ~1e2..1e3, which amplifies the last-bit logf differences to ~1e-6 relative
+    assert np.allclose(got, ref, rtol=2e-5, atol=0, equal_nan=True), (got, ref)
+    print(f"deviance C={C} m={m}: identical {int((got == ref).sum())}/{m}, max rel {np.max(np.abs(got - ref) / np.abs(ref)):.1e}")
