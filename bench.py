@@ -377,6 +377,8 @@ def main():
         raise SystemExit("bench.py (native arm) needs a CUDA device: the hot path has no CPU fallback")
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line (NCCL prints its banner there)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

@@ -152,7 +152,133 @@ mi_cc_pairs_kernel(const double *__restrict__ XR, const double *__restrict__ YR,
         __syncwarp();
         if (lane < 2) {
             const double *src = lane == 0 ? sx[w] : sy[w];
-            auto get = [&](int s) -> double { return src[s]; };
+            auto get = [&](int64_t s) -> double { return src[s]; };
+            const double mean = np_pairwise_sum<double>(get, 0, n) / (double)n;
+            const double other = __shfl_sync(0x3u, mean, 1);
+            if (lane == 0) {
+                double mi = ((psi_n + psi_k) - mean) - other;
+                mi = mi > 0.0 ? mi : 0.0;
+                mi_condensed[q] = mi;
+                if (dense != nullptr) { dense[i * N + j] = mi; dense[j * N + i] = mi; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gc_mi_cc_pairs_sorted: the same estimator with 1-D sorted orders prepared once per gene.  The k-th neighbour
+// search of sample s walks outward from s in x-sorted order and stops as soon as the next |dx| cannot beat the
+// current third-smallest Chebyshev distance (every unvisited point has d >= |dx|), ~13 candidates instead of 49 for
+// n = 50; the marginal counts are run lengths in the x- resp. y-sorted arrays.  Distances, radii and counts are the
+// brute-force kernel's bit for bit (same subtractions, same order statistic); tests compare the two kernels.
+// Measured SLOWER than brute force on GeneClust's 50-d PCA embeddings (50.9 vs 37.7 ms per 7 998 000 pairs: isolated
+// large-coordinate samples walk the whole array and every warp waits for its slowest lane), so it serves as the
+// independent cross-check, not as the production path.
+// ---------------------------------------------------------------------------------------------------------
+// one thread per (row, role): stable insertion sort of the row; sorted values, order (sample id at position) and
+// rank (position of sample) as uint8, rows padded to 64
+__global__ void mi_sort_rows_kernel(const double *__restrict__ XR, const double *__restrict__ YR, int64_t N, int n,
+                                    int64_t ldr, double *__restrict__ xs, uint8_t *__restrict__ xo,
+                                    double *__restrict__ ys, uint8_t *__restrict__ yrank) {
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const bool is_y = blockIdx.y == 1;
+    const double *src = (is_y ? YR : XR) + g * ldr;
+    double v[64];
+    uint8_t id[64];
+    for (int s = 0; s < n; ++s) {
+        const double x = src[s];
+        int p = s;
+        while (p > 0 && v[p - 1] > x) { v[p] = v[p - 1]; id[p] = id[p - 1]; --p; }    // strict >: stable
+        v[p] = x; id[p] = (uint8_t)s;
+    }
+    double *dst = (is_y ? ys : xs) + g * 64;
+    for (int p = 0; p < n; ++p) dst[p] = v[p];
+    if (is_y) { for (int p = 0; p < n; ++p) yrank[g * 64 + id[p]] = (uint8_t)p; }
+    else { for (int p = 0; p < n; ++p) xo[g * 64 + p] = id[p]; }
+}
+
+// k = 3 neighbour radius and marginal counts of the sample at x-sorted position p (y-sorted position yr)
+__device__ __forceinline__ void ksg_sample_sorted(const double *__restrict__ Xs, const double *__restrict__ Yx,
+                                                  const double *__restrict__ Ys, int n, int p, int yr, int &nx, int &ny) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const double xp = Xs[p], yp = Yx[p];
+    int l = p - 1, r = p + 1;
+    double m0 = INF, m1 = INF, m2 = INF;
+    double dl = l >= 0 ? xp - Xs[l] : INF, dr = r < n ? Xs[r] - xp : INF;
+    while (true) {
+        const bool take_l = dl <= dr;
+        const double dx = take_l ? dl : dr;
+        if (!(dx < m2)) break;                     // every unvisited point has d >= |dx| >= the current third smallest
+        const int q = take_l ? l : r;
+        const double d = fmax(dx, fabs(yp - Yx[q]));
+        insert3(d, m0, m1, m2);
+        if (take_l) { --l; dl = l >= 0 ? xp - Xs[l] : INF; }
+        else { ++r; dr = r < n ? Xs[r] - xp : INF; }
+    }
+    const double rad = next_toward_zero(m2);
+    int c = 1;                                     // counts include the point itself, as in the brute-force kernel
+    for (int q = p - 1; q >= 0 && xp - Xs[q] <= rad; --q) ++c;
+    for (int q = p + 1; q < n && Xs[q] - xp <= rad; ++q) ++c;
+    nx = c;
+    c = 1;
+    for (int q = yr - 1; q >= 0 && yp - Ys[q] <= rad; --q) ++c;
+    for (int q = yr + 1; q < n && Ys[q] - yp <= rad; ++q) ++c;
+    ny = c;
+}
+
+__global__ void __launch_bounds__(kPairWarps * 32)
+mi_cc_pairs_sorted_kernel(const double *__restrict__ YR, long long N, int n, int64_t ldr,
+                          const double *__restrict__ XS, const uint8_t *__restrict__ XO,
+                          const double *__restrict__ YS, const uint8_t *__restrict__ YRK,
+                          const double *__restrict__ psi, long long p_begin, long long p_end,
+                          double *__restrict__ mi_condensed, double *__restrict__ dense, uint8_t *__restrict__ nx_out,
+                          uint8_t *__restrict__ ny_out) {
+    __shared__ double sXs[kPairWarps][64];     // x, x-sorted
+    __shared__ double sYx[kPairWarps][64];     // y of the sample at each x-sorted position
+    __shared__ double sYs[kPairWarps][64];     // y, y-sorted
+    __shared__ double sP[kPairWarps][64];      // psi(nx + 1) by sample id
+    __shared__ double sQ[kPairWarps][64];      // psi(ny + 1) by sample id
+    __shared__ double spsi[65];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int m = threadIdx.x; m <= n; m += blockDim.x) spsi[m] = psi[m];
+    __syncthreads();
+    const double psi_n = spsi[n], psi_k = spsi[3];
+    const bool v0 = lane < n, v1 = lane + 32 < n;
+
+    const long long n_pairs = p_end - p_begin;
+    const long long warp_global = (long long)blockIdx.x * kPairWarps + w;
+    const long long n_warps = (long long)gridDim.x * kPairWarps;
+    for (long long q = warp_global; q < n_pairs; q += n_warps) {
+        long long i, j;
+        pair_from_index(p_begin + q, N, i, j);
+        const double *yg = YR + j * ldr;
+        int sid0 = 0, sid1 = 0, yr0 = 0, yr1 = 0;
+        __syncwarp();
+        if (v0) {
+            sid0 = XO[i * 64 + lane];
+            sXs[w][lane] = XS[i * 64 + lane]; sYx[w][lane] = yg[sid0]; sYs[w][lane] = YS[j * 64 + lane];
+            yr0 = YRK[j * 64 + sid0];
+        }
+        if (v1) {
+            sid1 = XO[i * 64 + lane + 32];
+            sXs[w][lane + 32] = XS[i * 64 + lane + 32]; sYx[w][lane + 32] = yg[sid1]; sYs[w][lane + 32] = YS[j * 64 + lane + 32];
+            yr1 = YRK[j * 64 + sid1];
+        }
+        __syncwarp();
+        int nxa = 1, nya = 1, nxb = 1, nyb = 1;
+        if (v0) ksg_sample_sorted(sXs[w], sYx[w], sYs[w], n, lane, yr0, nxa, nya);
+        if (v1) ksg_sample_sorted(sXs[w], sYx[w], sYs[w], n, lane + 32, yr1, nxb, nyb);
+        if (nx_out != nullptr) {
+            if (v0) { nx_out[q * n + sid0] = (uint8_t)(nxa - 1); ny_out[q * n + sid0] = (uint8_t)(nya - 1); }
+            if (v1) { nx_out[q * n + sid1] = (uint8_t)(nxb - 1); ny_out[q * n + sid1] = (uint8_t)(nyb - 1); }
+        }
+        if (v0) { sP[w][sid0] = spsi[nxa]; sQ[w][sid0] = spsi[nya]; }
+        if (v1) { sP[w][sid1] = spsi[nxb]; sQ[w][sid1] = spsi[nyb]; }
+        __syncwarp();
+        if (lane < 2) {
+            const double *src = lane == 0 ? sP[w] : sQ[w];
+            auto get = [&](int64_t s) -> double { return src[s]; };
             const double mean = np_pairwise_sum<double>(get, 0, n) / (double)n;
             const double other = __shfl_sync(0x3u, mean, 1);
             if (lane == 0) {
@@ -339,6 +465,40 @@ extern "C" int gc_mi_cc_pairs(const double *XR, const double *YR, int64_t N, int
         XR, YR, N, n, ldr, psi, p_begin, p_end, mi_condensed, dense, nx_out, ny_out);
     prof_end(kProfMiPairs, as_stream(stream));
     return check_launch("mi_cc_pairs_kernel");
+}
+
+extern "C" int64_t gc_mi_cc_pairs_scratch_bytes(int64_t N, int n) {
+    (void)n;
+    return 2 * N * 64 * 8 + 2 * N * 64 + 512;
+}
+
+extern "C" int gc_mi_cc_pairs_sorted(const double *XR, const double *YR, int64_t N, int n, int64_t ldr, const double *psi,
+                                     int64_t p_begin, int64_t p_end, double *mi_condensed, double *dense,
+                                     uint8_t *nx_out, uint8_t *ny_out, void *scratch, void *stream) {
+    GC_REQUIRE(XR && YR && psi && mi_condensed && scratch, "null pointer");
+    GC_REQUIRE(n >= 4 && n <= 64, "n must be in [4, 64] (k = 3 neighbours)");
+    GC_REQUIRE(N >= 2 && ldr >= n, "bad shape");
+    GC_REQUIRE(p_begin >= 0 && p_end >= p_begin && p_end <= N * (N - 1) / 2, "pair range out of bounds");
+    GC_REQUIRE((nx_out == nullptr) == (ny_out == nullptr), "nx_out and ny_out must be given together");
+    GC_REQUIRE(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+    if (p_end == p_begin) return 0;
+    cudaStream_t st = as_stream(stream);
+    char *p = (char *)scratch;
+    double *xs = (double *)p;     p += N * 64 * 8;
+    double *ys = (double *)p;     p += N * 64 * 8;
+    uint8_t *xo = (uint8_t *)p;   p += N * 64;
+    uint8_t *yrank = (uint8_t *)p;
+    mi_sort_rows_kernel<<<dim3((unsigned)ceil_div<int64_t>(N, 64), 2), 64, 0, st>>>(XR, YR, N, n, ldr, xs, xo, ys, yrank);
+    if (int rc = check_launch("mi_sort_rows_kernel")) return rc;
+    const long long n_pairs = p_end - p_begin;
+    long long blocks = ceil_div<long long>(n_pairs, kPairWarps);
+    const long long cap = (long long)kNumSMs * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    prof_begin(kProfMiPairs, st);
+    mi_cc_pairs_sorted_kernel<<<(unsigned)blocks, kPairWarps * 32, 0, st>>>(YR, N, n, ldr, xs, xo, ys, yrank, psi, p_begin, p_end,
+                                                                           mi_condensed, dense, nx_out, ny_out);
+    prof_end(kProfMiPairs, st);
+    return check_launch("mi_cc_pairs_sorted_kernel");
 }
 
 extern "C" int gc_mi_cc_problems(const double *XR, const double *YR, const int64_t *x_off, const int64_t *y_off,

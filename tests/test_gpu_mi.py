@@ -157,3 +157,32 @@ def test_complementarity_golden_bit_exact(torch_cuda, golden_dir):
     g = _load(golden_dir, "complementarity_small.npz")
     got = gene_complementarity(torch.from_numpy(g["Z"]).cuda(), g["labels"], g["edges"], int(g["seed"]))
     assert np.array_equal(got, g["complementarity"])
+
+
+@pytest.mark.parametrize("n", [50, 64, 33, 7])
+def test_sorted_scan_pairs_equal_brute_force(torch_cuda, n):
+    """Two independent device implementations of the KSG pair estimator - the production brute-force kernel and the
+    sorted outward scan with early exit - against each other and the numpy oracle: neighbour counts nx, ny and MI
+    bit-identical, incl. duplicate values (ties) and tiny n."""
+    torch = torch_cuda
+    from oracle import mi_bruteforce as mb
+    from scgeneclust_b200.tl.information import gene_redundancy
+    rs = np.random.RandomState(n)
+    N = 300
+    E = (rs.standard_normal((N, n)) * (2.0 / np.sqrt(1 + np.arange(n)))).astype(np.float32)
+    E[:40] = np.round(E[:40], 1)                       # heavy ties in 40 genes
+    E[40:50, : n // 2] = E[40:50, n // 2: 2 * (n // 2)]  # exact duplicates inside a gene
+    Ed = torch.from_numpy(E).cuda()
+    c_s, D_s, nx_s, ny_s = gene_redundancy(Ed, 3, return_counts=True, sorted_scan=True)
+    c_b, D_b, nx_b, ny_b = gene_redundancy(Ed, 3, return_counts=True)
+    assert torch.equal(nx_s, nx_b) and torch.equal(ny_s, ny_b)
+    assert torch.equal(c_s, c_b) and torch.equal(D_s, D_b)
+    xi1, xi2 = mb.noise_vectors(n, 3)
+    XR = np.stack([mb.prep_feature(e, xi1) for e in E[:60]])
+    YR = np.stack([mb.prep_target(e, xi2) for e in E[:60]])
+    pairs = np.stack(np.triu_indices(60, 1), 1)
+    nx_o, ny_o, mi_o = mb.ksg_batch(XR, YR, pairs)
+    iu = np.triu_indices(N, 1)
+    sel = np.flatnonzero((iu[0] < 60) & (iu[1] < 60))
+    assert np.array_equal(nx_s.cpu().numpy()[sel], nx_o) and np.array_equal(ny_s.cpu().numpy()[sel], ny_o)
+    assert np.array_equal(c_s.cpu().numpy()[sel], mi_o)
