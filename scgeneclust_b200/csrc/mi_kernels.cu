@@ -122,7 +122,7 @@ mi_cc_pairs_kernel(const double *__restrict__ XR, const double *__restrict__ YR,
         __syncwarp();
 
         double a0 = INF, a1 = INF, a2 = INF, b0 = INF, b1 = INF, b2 = INF;
-#pragma unroll 2
+#pragma unroll 5
         for (int t = 0; t < n; ++t) {
             const double xt = sx[w][t], yt = sy[w][t];
             double da = fmax(fabs(xs0 - xt), fabs(ys0 - yt));
@@ -134,7 +134,7 @@ mi_cc_pairs_kernel(const double *__restrict__ XR, const double *__restrict__ YR,
         }
         const double ra = next_toward_zero(a2), rb = next_toward_zero(b2);
         int nxa = 0, nya = 0, nxb = 0, nyb = 0;
-#pragma unroll 2
+#pragma unroll 5
         for (int t = 0; t < n; ++t) {
             const double xt = sx[w][t], yt = sy[w][t];
             nxa += fabs(xs0 - xt) <= ra; nya += fabs(ys0 - yt) <= ra;
