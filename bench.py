@@ -328,7 +328,18 @@ def run_native(args, rank: int, world: int, local_rank: int):
         L.profile_collect(1, ctypes.byref(tot), ctypes.byref(cnt))
         p_ms = max(p_dev_ms, p_wall_ms) / 3
         n = E.shape[1]
+        # roofline of the KSG pair kernel: fp64 / integer issue bound; denominator = the DFMA issue rate measured on
+        # this GPU right now (MEASURED_PEAKS.json has no fp64 figure); algorithmic work = 8 n^2 fp64-class ops per pair
+        peak64 = ctypes.c_double()
+        probe_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+        L.fp64_probe(ctypes.byref(peak64), probe_buf.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        k_ms = tot.value / max(cnt.value, 1)
+        ops = 8.0 * n * n * (hi - lo) / (k_ms * 1e-3)
         line["ps_redundancy"] = {
+            "roofline": {"kernel": "mi_cc_pairs_kernel", "bound": "fp64-issue", "achieved": ops / 1e12,
+                         "peak": peak64.value / 1e12, "unit": "T fp64-class op/s", "frac": ops / peak64.value,
+                         "peak_source": "gc_fp64_probe (DFMA lane-ops/s measured in this run)",
+                         "algorithmic_ops_per_pair": 8.0 * n * n},
             "metric": "gene-pairs/s", "value": n_pairs_total / (p_ms * 1e-3), "pairs": n_pairs_total,
             "genes": int(E.shape[0]), "samples_per_gene": int(n), "ms": p_ms,
             "kernel_ms": tot.value / max(cnt.value, 1),

@@ -39,6 +39,11 @@ long long gc_launch_count(void);
 int gc_profile_enable(int on);
 int gc_profile_collect(int slot, double *total_ms_host, long long *launches_host);
 
+/* Measured fp64 issue rate of this GPU (DFMA lane-operations per second, 8 independent chains per thread, all SMs):
+ * the roofline denominator bench.py uses for the kNN mutual-information kernels, which are fp64 / integer issue bound
+ * (SURVEY.md section 8d).  scratch_dev: 8 bytes of device memory.  Synchronises the stream. */
+int gc_fp64_probe(double *ops_per_s_host, double *scratch_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Ingest.  Replaces the host densification at scGeneClust/_model.py:123-124 and the integer check at
  * scGeneClust/_validation.py:68-70.

@@ -56,6 +56,42 @@ extern "C" int gc_profile_collect(int slot, double *total_ms, long long *launche
     return 0;
 }
 
+// fp64 issue-rate probe: every thread runs `iters` x 8 independent DFMA chains; the MI kernels' roofline denominator
+// (MEASURED_PEAKS.json has no fp64 figure, so it is measured on the box)
+namespace gc {
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) out[0] = s;        // never true: keeps the chains alive
+}
+}  // namespace gc
+
+extern "C" int gc_fp64_probe(double *ops_per_s_host, double *scratch_dev, void *stream) {
+    GC_REQUIRE(ops_per_s_host && scratch_dev, "null pointer");
+    cudaStream_t st = gc::as_stream(stream);
+    const int iters = 4096, blocks = gc::kNumSMs * 8;
+    cudaEvent_t e0, e1;
+    GC_CUDA(cudaEventCreate(&e0));
+    GC_CUDA(cudaEventCreate(&e1));
+    gc::fp64_probe_kernel<<<blocks, 256, 0, st>>>(scratch_dev, iters, 1.0);           // warm-up
+    GC_CUDA(cudaEventRecord(e0, st));
+    gc::fp64_probe_kernel<<<blocks, 256, 0, st>>>(scratch_dev, iters, 2.0);
+    GC_CUDA(cudaEventRecord(e1, st));
+    GC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    gc::g_launches.fetch_add(2, std::memory_order_relaxed);
+    *ops_per_s_host = (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3);      // DFMA instructions (lane-ops) per second
+    return 0;
+}
+
 extern "C" int gc_abi_version(void) { return GC_ABI_VERSION; }
 extern "C" const char *gc_last_error(void) { return gc::g_err; }
 extern "C" long long gc_launch_count(void) { return gc::g_launches.load(); }
