@@ -41,7 +41,8 @@ constexpr int TC_PRODUCER_WARPS = 16;
 constexpr int TC_GROUP_WARPS = TC_PRODUCER_WARPS / TC_GROUPS;
 constexpr int TC_PRODUCERS = TC_PRODUCER_WARPS * 32;
 constexpr int TC_THREADS = TC_PRODUCERS + 64;
-constexpr int TC_CHUNKS = 8;         // 16-byte count chunks per producer thread and stage
+constexpr int TC_CHUNKS = 1024 / (TC_GROUP_WARPS * 32);   // 16-byte count chunks per producer thread and stage
+constexpr int TC_EPI_WARPS = 16;     // producer warps that also run the epilogue (4 TMEM lane groups x 4 column quarters)
 constexpr int TC_A_BYTES = TC_TM * TC_TK * 2;      // 16 KB per half (hi or lo)
 constexpr int TC_B_BYTES = TC_TN * TC_TK * 2;      // 8 KB per half
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 48 KB
@@ -348,9 +349,9 @@ rsvd_apply_tc_kernel(const TcArgs a) {
         const int group = warp / TC_GROUP_WARPS, tg = tid & (TC_GROUP_WARPS * 32 - 1);
         const int a_col = TRANS == 0 ? (tg & 7) : (tg & 15);
         const int a_row0 = TRANS == 0 ? (tg >> 3) : (tg >> 4);
-        constexpr int A_ROW_STEP = TRANS == 0 ? 16 : 8;
+        constexpr int A_ROW_STEP = TRANS == 0 ? TC_GROUP_WARPS * 32 / 8 : TC_GROUP_WARPS * 32 / 16;
         // shared-memory chunk offsets are affine in j (row + 16 j / cell + 8 j keeps row & 7): base + immediate
-        constexpr uint32_t A_OFF_STEP = TRANS == 0 ? 2048u : 1024u;
+        constexpr uint32_t A_OFF_STEP = (uint32_t)(A_ROW_STEP / 8) * 1024u;
         const uint32_t a_off0 = TRANS == 0 ? swz128(a_row0, a_col)
                                            : (uint32_t)(a_col >> 3) * 8192u + swz128(a_row0, a_col & 7);
         const int32_t c_last = (int32_t)(a.C - 1);
@@ -437,6 +438,8 @@ rsvd_apply_tc_kernel(const TcArgs a) {
             mbar_wait(bar_accum, 0);
             tc_fence_after();
         }
+        if (warp >= TC_EPI_WARPS) goto epilogue_done;
+        {
         const int lane_grp = warp & 3, col_q = warp >> 2;
         float acc[16];
 #pragma unroll
@@ -459,6 +462,8 @@ rsvd_apply_tc_kernel(const TcArgs a) {
             for (int j = 0; j < 4; ++j)
                 dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
+        }
+    epilogue_done:;
     } else if (warp == TC_PRODUCER_WARPS) {
         // =============================== MMA issuer (whole warp, one elected lane issues) =============
         {
