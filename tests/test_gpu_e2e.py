@@ -167,3 +167,50 @@ def test_device_deviance_equals_numpy(torch_cuda, C, m):
     # left and right halves (~1e4) cancel to ~1e2..1e3, which amplifies the last-bit logf differences to ~1e-6 relative
     assert np.allclose(got, ref, rtol=2e-5, atol=0, equal_nan=True), (got, ref)
     print(f"deviance C={C} m={m}: identical {int((got == ref).sum())}/{m}, max rel {np.max(np.abs(got - ref) / np.abs(ref)):.1e}")
+
+
+def test_fast_c1_shape_more_genes_than_cells_vs_oracle(torch_cuda):
+    """BASELINE.json config c1 shape class (pbmc3k: 2 700 cells, ~13 700 genes after the loader's min_cells=3 filter;
+    the real file is not shipped, so a synthetic matrix of that shape): sklearn does NOT transpose here, the randomized
+    solver runs the passes the other way round; ragged sizes (not multiples of 64 / 128)."""
+    from sklearn.metrics import adjusted_rand_score
+    from oracle import stages
+    from oracle.synth import synth_counts
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    from scgeneclust_b200.synth import synth_params
+    p = synth_params(6001, 1)
+    X = np.concatenate([synth_counts(p, c0, min(450, 1350 - c0), 0, 6001) for c0 in range(0, 1350, 450)])
+    keep = (X > 0).sum(0) >= 3
+    X = np.ascontiguousarray(X[:, keep])
+    assert X.shape[1] > X.shape[0]
+    names = np.array([f"g{i}" for i in np.flatnonzero(keep)], dtype=object)
+    K = 30
+    ref = stages.geneclust_fast(X, names, K, 0)
+    info, sel = scGeneClust(AnnDataLite(X.astype(np.float32), var_names=names), n_var_clusters=K, version='fast',
+                            return_info=True, verbosity=0)
+    rel = np.linalg.norm(info.varm['X_pca'] - ref['X_pca'], axis=0) / np.linalg.norm(ref['X_pca'], axis=0)
+    ari = adjusted_rand_score(info.var['cluster'].to_numpy(), ref['labels'])
+    print(f"c1-shape fast: {X.shape}, PCA rel err {rel.max():.2e}, ARI {ari:.4f}, identical list "
+          f"{np.array_equal(sel, ref['selected'])}")
+    assert rel.max() <= 1e-3 and ari >= 0.9
+
+
+def test_argument_errors_match_reference(torch_cuda):
+    """Error types / messages of scGeneClust/_validation.py, raised before any device work."""
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    ad = AnnDataLite(np.ones((4, 5), np.float32))
+    with pytest.raises(ValueError, match="version"):
+        scGeneClust(ad, version='slow', n_var_clusters=3)
+    with pytest.raises(TypeError, match="n_gene_clusters"):
+        scGeneClust(ad, version='fast')
+    with pytest.raises(ValueError, match="> 1"):
+        scGeneClust(ad, version='fast', n_var_clusters=1)
+    with pytest.raises(ValueError, match="spatial"):
+        scGeneClust(ad, version='fast', n_var_clusters=3, modality='st')
+    with pytest.raises(TypeError, match="AnnData"):
+        scGeneClust(np.ones((4, 5)), version='fast', n_var_clusters=3)
+    with pytest.raises(TypeError, match="n_obs_clusters"):
+        scGeneClust(ad, version='ps')
+    ad.raw = object()
+    with pytest.raises(ValueError, match="raw"):
+        scGeneClust(ad, version='fast', n_var_clusters=3)
