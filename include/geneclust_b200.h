@@ -215,6 +215,14 @@ int gc_mi_cc_problems(const double *XR, const double *YR, const int64_t *x_off, 
 int gc_mi_cd(const double *XR, int64_t ldr, int64_t G, int n, const int32_t *label, const int32_t *label_k,
              int n_label, double const_term, const double *psi, int32_t *m_all, double *mi, void *stream);
 
+/* Maximum-redundancy spanning forest of the graph with an edge wherever R != 0 (R: dense symmetric N x N float64 on
+ * the device) - igraph Weighted_Adjacency(-R).spanning_tree at scGeneClust/tl/information.py:124-126.  Boruvka under
+ * the strict edge order (larger R first, ties by smaller i*N + j, i < j), so the forest is unique.  edges_out:
+ * (N - 1) x 2 int32 (unordered; sort by (i, j) for igraph's edge order), n_edges_out[0] = number of edges found
+ * (N - 1 iff the graph is connected).  scratch: gc_mst_scratch_bytes(N), 256-byte aligned.  No host synchronisation. */
+int64_t gc_mst_scratch_bytes(int64_t N);
+int gc_mst_boruvka(const double *R, int64_t N, int32_t *edges_out, int32_t *n_edges_out, void *scratch, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Synthetic negative-binomial counts (bench/test harness): counter-based, bit-identical
  * to oracle/synth.py.  Writes rows [c0, c0+nc) x genes [g0, g0+ng) of the global matrix into counts[nc x ld].

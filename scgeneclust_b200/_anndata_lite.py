@@ -24,12 +24,55 @@ except Exception:  # noqa: BLE001
     _REAL_ANNDATA = ()
 
 
+class DeviceMatrix:
+    """A dense float32 matrix that lives on the device and stands in for `adata.X` (the Pearson residuals) until a host
+    array is really needed: `np.asarray(x)` downloads it, `x[:, idx]` / `x[idx, :]` subset on the device.  GeneClust-ps
+    subsets the residual matrix twice (high-confidence cells, relevant genes; scGeneClust/tl/confidence.py:75-76,
+    tl/information.py:53-54) before anything reads it on the host - at config c4 the eager copy was 0.8 GB of
+    pageable D2H plus two host fancy-index copies."""
+    ndim = 2
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.tensor.cpu().numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def copy(self):
+        return DeviceMatrix(self.tensor.clone())
+
+    def __getitem__(self, key):
+        import torch
+        if not (isinstance(key, tuple) and len(key) == 2):
+            return np.asarray(self)[key]
+        t = self.tensor
+        for axis, k in enumerate(key):
+            if isinstance(k, slice) and k == slice(None):
+                continue
+            k = np.asarray(k)
+            if k.dtype == bool:
+                k = np.flatnonzero(k)
+            if k.ndim != 1 or k.dtype.kind not in "iu":
+                return np.asarray(self)[key]
+            t = t.index_select(axis, torch.from_numpy(k.astype(np.int64)).to(t.device))
+        return DeviceMatrix(t.contiguous())
+
+
 class AnnDataLite:
     """`n_obs` x `n_vars` annotated matrix: `.X`, `.obs`, `.var`, `.obsm`, `.varm`, `.obsp`, `.varp`, `.uns`."""
 
     def __init__(self, X, obs: Optional[pd.DataFrame] = None, var: Optional[pd.DataFrame] = None,
                  obs_names=None, var_names=None):
-        if not (issparse(X) or isinstance(X, np.ndarray) or getattr(X, "is_device_counts", False)):
+        if not (issparse(X) or isinstance(X, (np.ndarray, DeviceMatrix)) or getattr(X, "is_device_counts", False)):
             X = np.asarray(X)
         if X.ndim != 2:
             raise ValueError(f"X must be 2-D, got shape {X.shape}")

@@ -65,13 +65,15 @@ SIGNATURES = {
     "gc_mi_cc_pairs_sorted": (C.c_int, [_p, _p, _i64, C.c_int, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "gc_mi_cc_problems": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p]),
     "gc_mi_cd": (C.c_int, [_p, _i64, _i64, C.c_int, _p, _p, C.c_int, _f64, _p, _p, _p, _p]),
+    "gc_mst_scratch_bytes": (_i64, [_i64]),
+    "gc_mst_boruvka": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "gc_synth_counts": (C.c_int, [_u64, _i64, _i64, _i64, _i64, _p, _p, C.c_int, _p, _p, C.c_int, _p, C.c_int,
                                   C.c_int, _p, _i64, _p]),
 }
 
 _NO_STATUS = {"gc_abi_version", "gc_last_error", "gc_launch_count", "gc_rsvd_scratch_bytes", "gc_gram_scratch_bytes",
               "gc_mt19937_normal_scratch_bytes", "gc_binomial_deviance_scratch_bytes", "gc_mi_cc_pairs_scratch_bytes",
-              "gc_kmeanspp_scratch_bytes"}
+              "gc_kmeanspp_scratch_bytes", "gc_mst_scratch_bytes"}
 
 
 class GeneClustLibError(RuntimeError):

@@ -82,5 +82,8 @@ def scGeneClust(
 
     logger.opt(colors=True).info(f"GeneClust-{version} finished.")
     if return_info:
+        from ._anndata_lite import DeviceMatrix
+        if isinstance(copied_adata.X, DeviceMatrix):          # hand the residuals back as the ndarray the reference returns
+            copied_adata.X = np.asarray(copied_adata.X)
         return copied_adata, selected_genes
     return selected_genes

@@ -54,7 +54,9 @@ def normalize(adata, modality: Literal['sc', 'st'] = 'sc', materialize: bool = F
         if st.comm is not None:
             raise NotImplementedError("dense residuals (GeneClust-ps / return_info) need the unsharded matrix")
         st.Z = st.op.materialize()
-        adata.X = st.Z.cpu().numpy()
+        from .._anndata_lite import AnnDataLite, DeviceMatrix
+        # AnnDataLite carries the device matrix itself (downloaded on first host use); a real AnnData needs an ndarray
+        adata.X = DeviceMatrix(st.Z) if isinstance(adata, AnnDataLite) else st.Z.cpu().numpy()
 
 
 def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):

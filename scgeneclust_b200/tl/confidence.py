@@ -26,10 +26,13 @@ def find_high_confidence_cells(adata, n_obs_clusters: int, n_components: int = 1
         keep = np.ones(adata.n_obs, bool)
     adata.obs['cluster'] = np.asarray(adata.obs['cluster']).astype(str)
     if not keep.all():
-        if st.Z is not None:
+        from .._anndata_lite import DeviceMatrix
+        adata._inplace_subset_obs(keep)
+        if isinstance(adata.X, DeviceMatrix):
+            st.Z = adata.X.tensor                    # the subset already happened on the device
+        elif st.Z is not None:
             import torch
             st.Z = st.Z.index_select(0, torch.from_numpy(np.flatnonzero(keep)).to(st.Z.device)).contiguous()
-        adata._inplace_subset_obs(keep)
     logger.opt(colors=True).info(
         f"Using <yellow>{adata.n_obs}</yellow> provided high-confidence cells in "
         f"<yellow>{len(np.unique(adata.obs['cluster']))}</yellow> pseudo cell types.")

@@ -37,6 +37,9 @@ def _noise(n: int, random_state: int, target: bool):
 
 
 def _device_matrix(adata, st, attr: str, host) -> torch.Tensor:
+    from .._anndata_lite import DeviceMatrix
+    if isinstance(host, DeviceMatrix):
+        return host.tensor
     t = getattr(st, attr, None)
     if t is not None and tuple(t.shape) == tuple(np.shape(host)):
         return t
@@ -96,7 +99,8 @@ def find_relevant_genes(adata, top_pct: int, max_workers: int = os.cpu_count() -
     adata._inplace_subset_var(is_relevant)
     adata.var['relevance'] = relevance[is_relevant]
     keep = torch.from_numpy(np.flatnonzero(is_relevant)).to(Z.device)
-    st.Z = Z.index_select(1, keep).contiguous()
+    from .._anndata_lite import DeviceMatrix
+    st.Z = adata.X.tensor if isinstance(adata.X, DeviceMatrix) else Z.index_select(1, keep).contiguous()
     if st.varm_pca is not None:
         st.varm_pca = st.varm_pca.index_select(0, keep).contiguous()
     logger.opt(colors=True).info(
@@ -199,6 +203,23 @@ def redundancy_mst(R: np.ndarray) -> np.ndarray:
     return np.stack([src[order], dst[order]], axis=1).astype(np.int64)
 
 
+def redundancy_mst_device(D: torch.Tensor) -> np.ndarray:
+    """The same spanning forest from the device-resident redundancy matrix (gc_mst_boruvka: Boruvka under the strict
+    edge order "larger MI first, ties by smaller upper-triangle edge id", which makes the forest unique).  With distinct
+    MI values it is the forest scipy / igraph find; among exactly tied values the three libraries may pick different,
+    equally heavy edges.  Returns (n_edges, 2) int64 sorted by (source, target), source < target."""
+    require_cuda()
+    L, stream = lib(), stream_handle()
+    N = D.shape[0]
+    assert D.dtype == torch.float64 and D.is_contiguous() and D.shape == (N, N)
+    edges = torch.empty((max(N - 1, 1), 2), dtype=torch.int32, device=D.device)
+    n_edges = torch.zeros(1, dtype=torch.int32, device=D.device)
+    scratch = torch.empty(L.mst_scratch_bytes(N), dtype=torch.uint8, device=D.device)
+    L.mst_boruvka(ptr(D), N, ptr(edges), ptr(n_edges), ptr(scratch), stream)
+    e = edges[:int(n_edges.item())].cpu().numpy().astype(np.int64)
+    return e[np.lexsort((e[:, 1], e[:, 0]))]
+
+
 # -------------------------------------------------------------------------------------------------------------
 # a8 complementarity
 # -------------------------------------------------------------------------------------------------------------
@@ -262,7 +283,11 @@ def compute_gene_complementarity(adata, max_workers: int = os.cpu_count() - 1, r
     logger.info("Computing gene complementarity...")
     st = get_state(adata)
     logger.debug("Building MST...")
-    adata.uns['mst_edges'] = redundancy_mst(adata.varp['redundancy'])
+    D = st.redundancy
+    if D is not None and tuple(D.shape) == tuple(np.shape(adata.varp['redundancy'])):
+        adata.uns['mst_edges'] = redundancy_mst_device(D)
+    else:
+        adata.uns['mst_edges'] = redundancy_mst(adata.varp['redundancy'])
     logger.debug("MST built.")
     Z = _device_matrix(adata, st, 'Z', adata.X)
     adata.uns['mst_edges_complm'] = gene_complementarity(Z, np.asarray(adata.obs['cluster']), adata.uns['mst_edges'],

@@ -92,7 +92,7 @@ def test_ps_stages_vs_oracle(torch_cuda, data):
     pp.reduce_dim(ad, 'ps', 0)
     find_high_confidence_cells(ad, 8)
     assert ad.n_obs == hc.sum()
-    Z = ad.X.copy()
+    Z = np.asarray(ad.X).copy()                  # adata.X is device-backed until a host array is asked for
     labels = np.asarray(ad.obs['cluster'])
     find_relevant_genes(ad, 20, 1, 0)
     rel_ref = stages.gene_relevance(Z, labels, 0)
@@ -111,7 +111,7 @@ def test_ps_stages_vs_oracle(torch_cuda, data):
     edges = ad.uns['mst_edges']
     assert edges.shape[1] == 2 and len(edges) <= ad.n_vars - 1
     sample = edges[:: max(1, len(edges) // 12)]
-    ref_c = stages.gene_complementarity(ad.X, labels, sample, 0)
+    ref_c = stages.gene_complementarity(np.asarray(ad.X), labels, sample, 0)
     assert np.array_equal(ad.uns['mst_edges_complm'][:: max(1, len(edges) // 12)], ref_c)
 
 

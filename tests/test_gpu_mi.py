@@ -186,3 +186,54 @@ def test_sorted_scan_pairs_equal_brute_force(torch_cuda, n):
     sel = np.flatnonzero((iu[0] < 60) & (iu[1] < 60))
     assert np.array_equal(nx_s.cpu().numpy()[sel], nx_o) and np.array_equal(ny_s.cpu().numpy()[sel], ny_o)
     assert np.array_equal(c_s.cpu().numpy()[sel], mi_o)
+
+
+def _kruskal_total_order(R):
+    """Spanning forest under the strict order (larger R first, ties by smaller upper-triangle edge id): host reference."""
+    N = R.shape[0]
+    iu = np.triu_indices(N, 1)
+    w = R[iu]
+    keep = np.flatnonzero(w != 0)
+    order = keep[np.lexsort((keep, -w[keep]))]
+    parent = list(range(N))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    out = []
+    for k in order:
+        a, b = int(iu[0][k]), int(iu[1][k])
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[ra] = rb
+            out.append((a, b))
+    out = np.array(sorted(out), dtype=np.int64).reshape(-1, 2)
+    return out
+
+
+@pytest.mark.parametrize("N,zero_frac,ties", [(300, 0.45, False), (257, 0.45, True), (120, 0.97, False), (2, 0.0, False)])
+def test_device_mst_equals_total_order_kruskal(torch_cuda, N, zero_frac, ties):
+    """Device Boruvka spanning forest of the MI > 0 graph: identical edge set to Kruskal under the same strict edge
+    order (so ties are resolved identically), same total weight as scipy's MST, forests when the graph is disconnected."""
+    torch = torch_cuda
+    from scipy.sparse.csgraph import connected_components
+    from scgeneclust_b200.tl.information import redundancy_mst, redundancy_mst_device
+    rs = np.random.RandomState(N)
+    A = rs.rand(N, N)
+    if ties:
+        A = np.round(A, 2)                                   # many exactly equal weights
+    A[rs.rand(N, N) < zero_frac] = 0.0
+    R = np.triu(A, 1)
+    R = R + R.T
+    got = redundancy_mst_device(torch.from_numpy(R).cuda())
+    ref = _kruskal_total_order(R)
+    assert np.array_equal(got, ref)
+    n_comp, _ = connected_components(R != 0, directed=False)
+    assert len(got) == N - n_comp
+    sp_edges = redundancy_mst(R)
+    assert len(sp_edges) == len(got)
+    assert np.isclose(R[got[:, 0], got[:, 1]].sum(), R[sp_edges[:, 0], sp_edges[:, 1]].sum(), rtol=1e-12)
+    if not ties:
+        assert np.array_equal(got, sp_edges)
