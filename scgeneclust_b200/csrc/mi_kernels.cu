@@ -4,6 +4,8 @@
 //
 // This translation unit is compiled with -fmad=false: every floating-point operation below must round exactly
 // like the numpy/sklearn expression it restates (no FMA contraction).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "np_sum.cuh"
 
@@ -405,6 +407,124 @@ mi_cd_counts_kernel(const double *__restrict__ XR, int64_t ldr, int64_t G, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same Ross counts in O(n log n) per gene: the 1-D estimator only needs, per sample, the k-th nearest value of
+// its own class and the number of values of any class within that radius.  One CTA per gene: bitonic sort of the
+// kept samples by value in shared memory; a stable partition by label gives every class its sorted sub-sequence, so
+// the k-th same-class neighbour is among the k predecessors / successors there; the global count is two binary
+// searches in the fully sorted array with the exact float64 predicate  v_s - v_t <= r  (monotone in v_t).
+// Distances, radii (nextafter) and counts are those of the brute-force kernel bit for bit; tests compare the two.
+// n <= 16384 (shared memory: 14 bytes per padded sample).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCdThreads = 1024;
+__global__ void __launch_bounds__(kCdThreads)
+mi_cd_counts_sorted_kernel(const double *__restrict__ XR, int64_t ldr, int64_t G, int n, int np2,
+                           const int32_t *__restrict__ label, const int32_t *__restrict__ label_k, int n_label,
+                           int32_t *__restrict__ m_all) {
+    extern __shared__ __align__(16) unsigned char cd_smem[];
+    double *V = reinterpret_cast<double *>(cd_smem);                          // [np2] values, sorted ascending
+    uint16_t *ID = reinterpret_cast<uint16_t *>(V + np2);                     // [np2] sample id at sorted position
+    uint16_t *CQ = ID + np2;                                                  // [np2] class-order position of sorted position
+    uint16_t *CPOS = CQ + np2;                                                // [np2] sorted position of class-order position
+    __shared__ int s_warp[32];
+    __shared__ int s_total, s_kept;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t g = blockIdx.x;
+    const double *c = XR + g * ldr;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    if (tid == 0) s_kept = 0;
+    __syncthreads();
+    int kept_local = 0;
+    for (int s = tid; s < np2; s += kCdThreads) {
+        bool kept = false;
+        if (s < n) {
+            kept = label_k[label[s]] > 0;
+            if (!kept) m_all[(int64_t)s * G + g] = 0;
+        }
+        V[s] = kept ? c[s] : INF;
+        ID[s] = (uint16_t)(s < n ? s : 0xFFFF);
+        kept_local += kept;
+    }
+    for (int o = 16; o > 0; o >>= 1) kept_local += __shfl_xor_sync(0xffffffffu, kept_local, o);
+    if (lane == 0 && kept_local) atomicAdd(&s_kept, kept_local);
+    __syncthreads();
+    const int nk = s_kept;                                                    // kept samples sort to [0, nk)
+    // ---- bitonic sort by value (ties in any order: equal values give equal distances and counts)
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += kCdThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double a = V[i], b = V[ixj];
+                    const bool up = (i & k) == 0;
+                    if (up ? (a > b) : (a < b)) {
+                        V[i] = b; V[ixj] = a;
+                        const uint16_t t = ID[i]; ID[i] = ID[ixj]; ID[ixj] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- stable partition by label: class l occupies class-order positions [off_l, off_l + cnt_l)
+    const int per = (nk + kCdThreads - 1) / kCdThreads;                       // contiguous slice per thread
+    const int p_lo = min(nk, tid * per), p_hi = min(nk, p_lo + per);
+    int off = 0;
+    for (int l = 0; l < n_label; ++l) {
+        if (label_k[l] <= 0) continue;
+        int cnt = 0;
+        for (int p = p_lo; p < p_hi; ++p) cnt += label[ID[p]] == l;
+        int incl = cnt;                                                       // warp inclusive scan
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+            int wi = w;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            s_warp[lane] = wi - w;                                            // exclusive warp offsets
+            if (lane == 31) s_total = wi;
+        }
+        __syncthreads();
+        int pos = off + s_warp[wid] + incl - cnt;
+        for (int p = p_lo; p < p_hi; ++p) {
+            if (label[ID[p]] == l) { CQ[p] = (uint16_t)pos; CPOS[pos] = (uint16_t)p; ++pos; }
+        }
+        off += s_total;
+        __syncthreads();
+    }
+    // ---- per sample: k-th same-class neighbour distance, then the global count within nextafter(radius)
+    for (int p = tid; p < nk; p += kCdThreads) {
+        const int sid = ID[p];
+        const int l = label[sid];
+        const int ks = label_k[l];
+        const double v = V[p];
+        const int q = CQ[p];
+        // class segment bounds: walk is bounded by k <= 3 steps, membership checked through the label of the neighbour
+        double dl[3] = {INF, INF, INF}, dr[3] = {INF, INF, INF};
+#pragma unroll
+        for (int j = 1; j <= 3; ++j) {
+            if (q - j >= 0) { const int pp = CPOS[q - j]; if (label[ID[pp]] == l) dl[j - 1] = v - V[pp]; }
+            if (q + j < nk) { const int pp = CPOS[q + j]; if (label[ID[pp]] == l) dr[j - 1] = V[pp] - v; }
+        }
+        // k-th smallest of the two ascending lists
+        int il = 0, ir = 0;
+        double eps = INF;
+        for (int t = 0; t < ks; ++t) {
+            const double a = il < 3 ? dl[il] : INF, b = ir < 3 ? dr[ir] : INF;
+            if (a <= b) { eps = a; ++il; } else { eps = b; ++ir; }
+        }
+        const double r = next_toward_zero(eps);
+        // smallest i in [0, p] with v - V[i] <= r ; largest j in [p, nk) with V[j] - v <= r
+        int lo = 0, hi = p;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (v - V[mid] <= r) hi = mid; else lo = mid + 1; }
+        const int first = lo;
+        lo = p; hi = nk - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (V[mid] - v <= r) lo = mid; else hi = mid - 1; }
+        m_all[(int64_t)sid * G + g] = lo - first + 1;
+    }
+}
+
 __global__ void mi_cd_finalize_kernel(const int32_t *__restrict__ m_all, int64_t G, int n,
                                       const int32_t *__restrict__ label, const int32_t *__restrict__ label_k,
                                       double const_term, const double *__restrict__ psi,
@@ -520,8 +640,23 @@ extern "C" int gc_mi_cd(const double *XR, int64_t ldr, int64_t G, int n, const i
                         double *mi, void *stream) {
     GC_REQUIRE(XR && label && label_k && psi && m_all && mi, "null pointer");
     GC_REQUIRE(G >= 1 && n >= 2 && ldr >= n && n_label >= 1, "bad shape");
-    mi_cd_counts_kernel<<<(unsigned)G, kProbThreads, 0, as_stream(stream)>>>(XR, ldr, G, n, label, label_k, m_all);
-    if (int rc = check_launch("mi_cd_counts_kernel")) return rc;
+    int np2 = 64;
+    while (np2 < n) np2 <<= 1;
+    static const bool force_brute = getenv("GC_MI_CD_BRUTE_FORCE") != nullptr;      // cross-check switch for the tests
+    if (n <= 16384 && !force_brute) {
+        const size_t smem = (size_t)np2 * 14;
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            GC_CUDA(cudaFuncSetAttribute(mi_cd_counts_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        mi_cd_counts_sorted_kernel<<<(unsigned)G, kCdThreads, smem, as_stream(stream)>>>(XR, ldr, G, n, np2, label, label_k,
+                                                                                      n_label, m_all);
+        if (int rc = check_launch("mi_cd_counts_sorted_kernel")) return rc;
+    } else {
+        mi_cd_counts_kernel<<<(unsigned)G, kProbThreads, 0, as_stream(stream)>>>(XR, ldr, G, n, label, label_k, m_all);
+        if (int rc = check_launch("mi_cd_counts_kernel")) return rc;
+    }
     mi_cd_finalize_kernel<<<(unsigned)ceil_div<int64_t>(G, 64), 64, 0, as_stream(stream)>>>(
         m_all, G, n, label, label_k, const_term, psi, mi);
     return check_launch("mi_cd_finalize_kernel");
