@@ -25,7 +25,8 @@ except Exception:  # noqa: BLE001
 
 
 class DeviceMatrix:
-    """A dense float32 matrix that lives on the device and stands in for `adata.X` (the Pearson residuals) until a host
+    """A dense matrix that lives on the device and stands in for `adata.X` (the Pearson residuals) or
+    `adata.varp['redundancy']` until a host
     array is really needed: `np.asarray(x)` downloads it, `x[:, idx]` / `x[idx, :]` subset on the device.  GeneClust-ps
     subsets the residual matrix twice (high-confidence cells, relevant genes; scGeneClust/tl/confidence.py:75-76,
     tl/information.py:53-54) before anything reads it on the host - at config c4 the eager copy was 0.8 GB of
@@ -41,7 +42,7 @@ class DeviceMatrix:
 
     @property
     def dtype(self):
-        return np.dtype(np.float32)
+        return np.dtype(str(self.tensor.dtype).replace("torch.", ""))
 
     def __array__(self, dtype=None, copy=None):
         a = self.tensor.cpu().numpy()

@@ -85,5 +85,9 @@ def scGeneClust(
         from ._anndata_lite import DeviceMatrix
         if isinstance(copied_adata.X, DeviceMatrix):          # hand the residuals back as the ndarray the reference returns
             copied_adata.X = np.asarray(copied_adata.X)
+        for slot in (copied_adata.varp, copied_adata.varm, copied_adata.obsm):
+            for key, value in list(slot.items()):
+                if isinstance(value, DeviceMatrix):
+                    slot[key] = np.asarray(value)
         return copied_adata, selected_genes
     return selected_genes

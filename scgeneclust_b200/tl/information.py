@@ -180,7 +180,9 @@ def compute_gene_redundancy(adata, max_workers: int = os.cpu_count() - 1, random
         D[iu[0], iu[1]] = full
         D = D + D.t()
     st.redundancy = D
-    adata.varp['redundancy'] = D.cpu().numpy()
+    from .._anndata_lite import AnnDataLite, DeviceMatrix
+    # 8 N^2 bytes (128 MB at N = 4000): stays on the device for the MST and the edge scaling; downloaded when read
+    adata.varp['redundancy'] = DeviceMatrix(D) if isinstance(adata, AnnDataLite) else D.cpu().numpy()
     logger.info("Gene redundancy computed.")
 
 
@@ -287,7 +289,7 @@ def compute_gene_complementarity(adata, max_workers: int = os.cpu_count() - 1, r
     if D is not None and tuple(D.shape) == tuple(np.shape(adata.varp['redundancy'])):
         adata.uns['mst_edges'] = redundancy_mst_device(D)
     else:
-        adata.uns['mst_edges'] = redundancy_mst(adata.varp['redundancy'])
+        adata.uns['mst_edges'] = redundancy_mst(np.asarray(adata.varp['redundancy']))
     logger.debug("MST built.")
     Z = _device_matrix(adata, st, 'Z', adata.X)
     adata.uns['mst_edges_complm'] = gene_complementarity(Z, np.asarray(adata.obs['cluster']), adata.uns['mst_edges'],

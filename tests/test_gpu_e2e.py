@@ -100,7 +100,7 @@ def test_ps_stages_vs_oracle(torch_cuda, data):
     assert np.array_equal(np.asarray(ad.var_names), names[mask])
     assert np.array_equal(ad.var['relevance'].to_numpy(), rel_ref[mask])
     compute_gene_redundancy(ad, 1, 0)
-    R = ad.varp['redundancy']
+    R = np.asarray(ad.varp['redundancy'])       # device-backed until read
     E = ad.varm['X_pca']
     rs = np.random.RandomState(0)
     pairs = np.sort(np.stack([rs.randint(0, len(E), 80), rs.randint(0, len(E), 80)], 1), 1)
