@@ -346,6 +346,32 @@ def run_native(args, rank: int, world: int, local_rank: int):
             "fp64_class_ops_per_s": 8.0 * n * n * (hi - lo) / (tot.value / max(cnt.value, 1) * 1e-3),
             "config": "BASELINE.json config c4 size: 4000 relevant genes x 50 PCs, k=3, pairs split over ranks"}
 
+    # GeneClust-ps through the public entry point at config c4 size (single GPU only: the ps path keeps the dense
+    # residuals of the high-confidence cells on one device): 10 000 cells x 20 000 genes from HOST counts, the
+    # generator's cell types as pseudo cell types, a deterministic 60 % of the cells marked high-confidence
+    if not args.no_ps and world == 1:
+        from scgeneclust_b200.synth import synth_cell_types
+        c4_cells = 10_000
+        Xc4 = synth.counts(0, c4_cells).to_numpy()
+        keep = (Xc4 > 0).sum(0) >= 3                                 # the reference loader's min_cells=3 filter (_utils.py:35)
+        Xc4 = np.ascontiguousarray(Xc4[:, keep])
+        names4 = names[keep]
+        types4 = np.array([f"type{t}" for t in synth_cell_types(params, 0, c4_cells)])
+        hc4 = np.random.RandomState(SEED).rand(c4_cells) < 0.6
+
+        def step_ps():
+            ad = AnnDataLite(Xc4, var_names=names4)
+            ad.obs['cluster'] = types4
+            ad.obs['highly_confident'] = hc4
+            return scGeneClust(ad, version='ps', n_obs_clusters=8, verbosity=0, random_state=SEED)
+        step_ps()
+        sel_ps, ps_dev_ms, ps_wall_ms = timed(step_ps, 3)
+        line["ps_end_to_end"] = {
+            "seconds": max(ps_dev_ms, ps_wall_ms) / 3 * 1e-3, "selected_genes": int(len(sel_ps)),
+            "config": f"BASELINE.json config c4: synthetic {c4_cells} cells x {int(keep.sum())} genes (of {G}, min_cells=3), "
+                      f"{int(hc4.sum())} high-confidence cells in 8 given pseudo cell types, relevant_gene_pct=20, "
+                      f"host counts -> selected genes through scGeneClust(version='ps')"}
+
     if rank == 0 and not args.no_cpu_baseline:
         n_cells = min(args.cpu_sample_cells, cells)
         Xs = synth_host_sample(params, n_cells, G)

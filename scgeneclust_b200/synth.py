@@ -67,3 +67,22 @@ class DeviceSynth:
                            ptr(self.module_levels), len(self.p.module_levels), self.p.n_modules, ptr(out), ld,
                            stream_handle())
         return DeviceCounts(out, nc, ng)
+
+
+def synth_cell_types(params: SynthParams, c0: int, nc: int) -> np.ndarray:
+    """Cell type the generator assigned to cells [c0, c0+nc): type = hash(seed, stream 1, cell) mod n_types, the same
+    integer hash `gc_synth_counts` evaluates on the device (csrc/synth_kernels.cu).  The bench uses these labels as the
+    given pseudo cell types of GeneClust-ps."""
+    u64 = np.uint64
+    m1, m2, gold = u64(0xBF58476D1CE4E5B9), u64(0x94D049BB133111EB), u64(0x9E3779B97F4A7C15)
+
+    def mix(z):
+        z = (z ^ (z >> u64(30))) * m1
+        z = (z ^ (z >> u64(27))) * m2
+        return z ^ (z >> u64(31))
+    cells = np.arange(c0, c0 + nc, dtype=u64)
+    with np.errstate(over="ignore"):
+        z = u64(params.seed) + gold * u64(2)
+        z = mix(z ^ (cells * m1))
+        z = mix(z ^ (np.zeros_like(cells) * m2))
+    return (z % u64(params.n_types)).astype(np.int32)
