@@ -178,7 +178,7 @@ def run_reference(args, rank: int):
                          "stage_s": {k: round(v, 3) for k, v in tm.items()}},
         "e2e": {"value": value, "unit": "matrix-entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def workload_config(args, n_gpus):
@@ -388,7 +388,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
             line["cpu_baseline"]["ps_sample"] = (f"{CPU_SAMPLE_PAIRS} random gene pairs, sklearn mutual_info_regression "
                                                  f"per pair in a {workers}-process pool (as the reference)")
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
 
 
 def step_embedding(scGeneClust, AnnDataLite, counts, names, args):
@@ -401,7 +401,46 @@ def step_embedding(scGeneClust, AnnDataLite, counts, names, args):
     return get_state(ad).varm_pca
 
 
+class _CleanStdout:
+    """stdout carries exactly one JSON line: native libraries (NCCL's version banner) write to file descriptor 1 too, so
+    fd 1 is pointed at stderr for the duration of the run and the line is written to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        self._out = os.fdopen(self._saved, "w")
+        return self
+
+    def emit(self, text: str):
+        self._out.write(text + "\n")
+        self._out.flush()
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        return False
+
+
+_STDOUT = None
+
+
+def emit_line(line: dict):
+    text = json.dumps(line)
+    if _STDOUT is not None:
+        _STDOUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global _STDOUT
+    with _CleanStdout() as _STDOUT:
+        _main()
+    _STDOUT = None
+
+
+def _main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -414,8 +453,6 @@ def main():
         raise SystemExit("bench.py (native arm) needs a CUDA device: the hot path has no CPU fallback")
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line (NCCL prints its banner there)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
