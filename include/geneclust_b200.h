@@ -155,6 +155,9 @@ int64_t gc_kmeanspp_scratch_bytes(int64_t n, int n_trials);
 int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, int K, int32_t first_center,
                      const double *uniforms, int n_trials, void *ws, float *centers_out, int32_t *indices_out,
                      void *stream);
+/* idx[i] = np.searchsorted(cdf, u[i], side='right') - the index stream of RandomState.choice(n, m, p=p) given its
+ * uniform draws u (MiniBatchKMeans mini-batch sampling, cluster/_kmeans.py:2169-2174).  cdf: float64[n] ascending. */
+int gc_searchsorted_right(const double *cdf, int64_t n, const double *u, int m, int32_t *idx, void *stream);
 /* out[0] = float64 sum of a float32 vector in a fixed order (batch inertia, cluster/_k_means_common.pyx:94-124). */
 int gc_sum_f32(const float *v, int64_t n, double *out, void *stream);
 /* dist[s] = |x_s - centers[labels[s]]|_2 (paired_distances, scGeneClust/tl/cluster.py:101). */

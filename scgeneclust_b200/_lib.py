@@ -54,6 +54,7 @@ SIGNATURES = {
     "gc_sqdist_to_rows": (C.c_int, [_p, _i64, _i64, C.c_int, _p, C.c_int, _p, _p]),
     "gc_kmeanspp_scratch_bytes": (_i64, [_i64, C.c_int]),
     "gc_kmeanspp_init": (C.c_int, [_p, _i64, _i64, C.c_int, C.c_int, _i32, _p, C.c_int, _p, _p, _p, _p]),
+    "gc_searchsorted_right": (C.c_int, [_p, _i64, _p, C.c_int, _p, _p]),
     "gc_sum_f32": (C.c_int, [_p, _i64, _p, _p]),
     "gc_paired_dist": (C.c_int, [_p, _i64, _i64, C.c_int, _p, _p, _p, _p]),
     "gc_closeness": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),

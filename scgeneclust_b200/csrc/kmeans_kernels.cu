@@ -510,6 +510,21 @@ __global__ void closeness_apply_kernel(const float *__restrict__ dist, const int
     out[s] = 1.0f - v;
 }
 
+// idx[i] = np.searchsorted(cdf, u[i], side='right') = first index with cdf[index] > u[i] (n if none): the mini-batch
+// sampling of RandomState.choice(n, size, p=p) given its uniform draws (numpy mtrand.pyx)
+__global__ void searchsorted_right_kernel(const double *__restrict__ cdf, int64_t n, const double *__restrict__ u, int m,
+                                          int32_t *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double x = u[i];
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cdf[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    idx[i] = (int32_t)lo;
+}
+
 // deterministic float64 sum of a float32 vector (single CTA, fixed tree), result as float64 and float32
 __global__ void __launch_bounds__(1024) sum_f32_kernel(const float *__restrict__ v, int64_t n, double *out) {
     __shared__ double red[1024];
@@ -592,6 +607,12 @@ extern "C" int gc_closeness(const float *dist, const int32_t *labels, int64_t n,
     if (int rc = check_launch("closeness_minmax_kernel")) return rc;
     closeness_apply_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, st>>>(dist, labels, n, K, scratch, closeness);
     return check_launch("closeness_apply_kernel");
+}
+
+extern "C" int gc_searchsorted_right(const double *cdf, int64_t n, const double *u, int m, int32_t *idx, void *stream) {
+    GC_REQUIRE(cdf && u && idx && n >= 1 && m >= 1, "bad arguments");
+    searchsorted_right_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, as_stream(stream)>>>(cdf, n, u, m, idx);
+    return check_launch("searchsorted_right_kernel");
 }
 
 extern "C" int gc_sum_f32(const float *v, int64_t n, double *out, void *stream) {

@@ -92,15 +92,18 @@ class DeviceMiniBatchKMeans:
         inertia_d = torch.empty(1, dtype=torch.float64, device=dev)
         idx = torch.empty(batch, dtype=torch.int32, device=dev)
         # pinned staging: one upload and one (two-part) read-back per step, a single stream synchronisation
-        idx_pin = torch.empty(batch, dtype=torch.int32).pin_memory()
+        u_pin = torch.empty(batch, dtype=torch.float64).pin_memory()
+        u_dev = torch.empty(batch, dtype=torch.float64, device=dev)
+        cdf_dev = torch.from_numpy(cdf).to(dev)
         counts_pin = torch.empty(K, dtype=torch.float32).pin_memory()
         inertia_pin = torch.empty(1, dtype=torch.float64).pin_memory()
         stream = torch.cuda.current_stream()
         step = 0
         for step in range(n_steps):
-            idx_h = cdf.searchsorted(rs.random_sample(batch), side='right')
-            idx_pin.numpy()[:] = idx_h
-            idx.copy_(idx_pin, non_blocking=True)
+            # the uniform draws go up, the searchsorted runs on the device against the same float64 cdf
+            u_pin.numpy()[:] = rs.random_sample(batch)
+            u_dev.copy_(u_pin, non_blocking=True)
+            L.searchsorted_right(ptr(cdf_dev), n, ptr(u_dev), batch, ptr(idx), st)
             # _random_reassign(), evaluated before the step on the counts of the previous one
             n_since_reassign += batch
             random_reassign = bool((counts_h == 0).any() or n_since_reassign >= 10 * K)
@@ -124,7 +127,7 @@ class DeviceMiniBatchKMeans:
                 n_reassigns = int(to_reassign.sum())
                 if n_reassigns:
                     picks = rs.choice(batch, replace=False, size=n_reassigns)
-                    rows = torch.from_numpy(idx_h[picks].astype(np.int64)).to(dev)
+                    rows = idx.index_select(0, torch.from_numpy(picks.astype(np.int64)).to(dev)).to(torch.int64)
                     centers_new[torch.from_numpy(np.flatnonzero(to_reassign)).to(dev)] = X.index_select(0, rows)
                     # the "dirty hack" count reset of _mini_batch_step (cluster/_kmeans.py:1679-1682); a no-op without
                     # reassigned centres
