@@ -277,6 +277,18 @@ class PanelAlgebra:
         return out
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    """One long-lived side stream per device (a fresh stream per call would give the caching allocator a fresh pool,
+    i.e. a cudaMalloc + device synchronisation, every call)."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
 def device_normal_panel(random_state: int, rows: int, q: int, device) -> torch.Tensor:
     """`np.random.RandomState(random_state).normal(size=(rows, q)).astype(np.float32)` as a zero-padded rows x 64
     device panel, generated on the device (gc_mt19937_normal_panel)."""
@@ -332,6 +344,19 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     n_iter = 7 if n_comps < 0.1 * min_dim else 4
     transpose = n_samples < n_features
 
+    fwd_is_stored = transpose if samples == "genes" else (not transpose)
+    n_in_total_early = G_total if fwd_is_stored else op.C
+    # Omega exactly as sklearn draws it (utils/extmath.py:323-334): normal((A.shape[1], q)) cast to float32 - the
+    # legacy RandomState stream is reproduced on the device from the seeded MT19937 state (20-40 ms on the host).
+    # Its word stream comes from ONE CTA (MT19937 is sequential), so it runs on a side stream underneath the
+    # residual-sum pass over the count matrix.
+    main_stream = torch.cuda.current_stream()
+    side_stream = _side_stream(dev)
+    side_stream.wait_stream(main_stream)
+    with torch.cuda.stream(side_stream):
+        Qp_full = device_normal_panel(random_state, n_in_total_early, q, dev)
+    omega_status = Qp_full._gc_status
+
     # centring vector = mean over samples of every feature (decomposition/_pca.py:733-735)
     if samples == "genes":
         zr, _ = op.residual_sums(rows=True, cols=False)
@@ -348,10 +373,11 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     # A.shape[1] = length of the Omega rows; trans=0 contracts genes, trans=1 contracts cells
     n_in_total = G_total if fwd == 0 else op.C
 
-    # Omega exactly as sklearn draws it (utils/extmath.py:323-334): normal((A.shape[1], q)) cast to float32 - the
-    # legacy RandomState stream is reproduced on the device from the seeded MT19937 state (20-40 ms on the host)
-    Qp = device_normal_panel(random_state, n_in_total, q, dev)
-    omega_status = Qp._gc_status
+    assert n_in_total == n_in_total_early
+    main_stream.wait_stream(side_stream)
+    Qp_full.record_stream(main_stream)
+    omega_status.record_stream(main_stream)
+    Qp = Qp_full
     if comm is not None and fwd == 0:
         Qp = Qp[comm.gene_lo:comm.gene_hi].contiguous()
 

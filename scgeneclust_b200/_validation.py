@@ -82,8 +82,9 @@ def check_gene_clustering(img, version, n_gene_clusters, n_obs_clusters, n_compo
 
 def check_all_genes_selected(adata, selected_genes: np.ndarray):
     # hash lookup instead of the reference's np.isin on object arrays (sort-based, ~70 ms for 20 000 names)
-    is_selected = adata.var_names.isin(selected_genes)
-    if (n_selected_genes := is_selected.sum()) != selected_genes.shape[0]:
+    wanted = set(np.asarray(selected_genes).tolist())
+    n_selected_genes = sum(map(wanted.__contains__, adata.var_names.tolist()))
+    if n_selected_genes != selected_genes.shape[0]:
         msg = f"Found only {n_selected_genes} selected genes in `adata.var_names`, not {selected_genes.shape[0]}."
         raise RuntimeError(msg)
     logger.opt(colors=True).info(f"Selected <yellow>{n_selected_genes}</yellow> genes.")
