@@ -48,7 +48,8 @@ chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, 
 // Symmetric eigendecomposition of the leading q x q block of Gm by cyclic two-sided Jacobi with the round-robin
 // parallel ordering.  Outputs eigenvalues in descending order (evals[64], zero padded) and the matching
 // eigenvectors as columns of U (float32 and float64, 64 x 64 row-major, zero padded).
-__global__ void __launch_bounds__(256)
+constexpr int kEigThreads = 1024;   // ~1800 row/column updates per Jacobi round: two per thread
+__global__ void __launch_bounds__(kEigThreads)
 sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals, float *__restrict__ U32,
                double *__restrict__ U64) {
     extern __shared__ double dyn_smem[];
@@ -57,27 +58,34 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
     __shared__ double cs[kN / 2][2];
     __shared__ int pp[kN / 2], qq[kN / 2];
     __shared__ double off2, diag2;
+    __shared__ double rowsum[kN];
     __shared__ int order[kN];
     const int tid = threadIdx.x;
     const int m = (q + 1) & ~1;          // even number of players (one dummy when q is odd)
     const int n_pairs = m / 2;
-    for (int idx = tid; idx < kN * kN; idx += 256) {
+    for (int idx = tid; idx < kN * kN; idx += kEigThreads) {
         const int r = idx / kN, c = idx % kN;
         A[r][c] = (r < q && c < q) ? Gm[r * kN + c] : 0.0;
         V[r][c] = r == c ? 1.0 : 0.0;
     }
     __syncthreads();
     for (int sweep = 0; sweep < 30; ++sweep) {
+        // off-diagonal / diagonal squared norms: thread r < q sums its row, thread 0 adds the q row sums in order
+        if (tid < q) {
+            double o = 0.0;
+            for (int c = tid + 1; c < q; ++c) o += A[tid][c] * A[tid][c];
+            rowsum[tid] = o;
+        }
+        __syncthreads();
         if (tid == 0) {
             double o = 0.0, d = 0.0;
-            for (int r = 0; r < q; ++r) {
-                d += A[r][r] * A[r][r];
-                for (int c = r + 1; c < q; ++c) o += A[r][c] * A[r][c];
-            }
+            for (int r = 0; r < q; ++r) { o += rowsum[r]; d += A[r][r] * A[r][r]; }
             off2 = o; diag2 = d;
         }
         __syncthreads();
-        if (off2 <= 1e-32 * diag2) break;
+        // 1e-27: the off-diagonal mass cannot fall below ~q^2 eps^2 = 2e-29 of the diagonal mass in float64, so a
+        // stricter test would only burn the remaining sweeps; at 1e-27 the eigenvectors are converged to ~3e-14
+        if (off2 <= 1e-27 * diag2) break;
         for (int round = 0; round < m - 1; ++round) {
             if (tid < n_pairs) {
                 // round-robin tournament: player m-1 fixed, the others rotate
@@ -95,7 +103,7 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
             }
             __syncthreads();
             // A <- A J  (columns), V <- V J
-            for (int task = tid; task < n_pairs * q; task += 256) {
+            for (int task = tid; task < n_pairs * q; task += kEigThreads) {
                 const int pr = task / q, r = task % q;
                 const int a = pp[pr], b = qq[pr];
                 if (b >= q) continue;
@@ -107,7 +115,7 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
             }
             __syncthreads();
             // A <- J^T A  (rows)
-            for (int task = tid; task < n_pairs * q; task += 256) {
+            for (int task = tid; task < n_pairs * q; task += kEigThreads) {
                 const int pr = task / q, col = task % q;
                 const int a = pp[pr], b = qq[pr];
                 if (b >= q) continue;
@@ -133,7 +141,7 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
     }
     __syncthreads();
     if (tid < kN) evals[tid] = tid < q ? A[order[tid]][order[tid]] : 0.0;
-    for (int idx = tid; idx < kN * kN; idx += 256) {
+    for (int idx = tid; idx < kN * kN; idx += kEigThreads) {
         const int r = idx / kN, c = idx % kN;
         const double v = (r < q && c < q) ? V[r][order[c]] : 0.0;
         U32[idx] = (float)v;
@@ -180,7 +188,7 @@ extern "C" int gc_sym_eig(const double *Gm, int q, double *evals, float *U32, do
         GC_CUDA(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    sym_eig_kernel<<<1, 256, smem, as_stream(stream)>>>(Gm, q, evals, U32, U64);
+    sym_eig_kernel<<<1, kEigThreads, smem, as_stream(stream)>>>(Gm, q, evals, U32, U64);
     return check_launch("sym_eig_kernel");
 }
 
