@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--clusters", type=int, default=K_CLUSTERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ps", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-resident arm (config c5 would pin 7.5 GB per rank)")
     ap.add_argument("--cpu-sample-cells", type=int, default=CPU_SAMPLE_CELLS)
     return ap.parse_args()
 
@@ -183,10 +184,16 @@ def run_reference(args, rank: int):
 
 def workload_config(args, n_gpus):
     cells = (args.cells or CELLS_PER_GPU) * n_gpus
+    if cells == 1_000_000 and args.genes == 30_000:
+        which = "BASELINE.json config c5"
+    elif (args.cells or CELLS_PER_GPU) == CELLS_PER_GPU and args.genes == GENES:
+        which = "BASELINE.json config c3 at N=1; cells scale with N"
+    else:
+        which = "custom size"
     return {"workload": f"GeneClust-fast, synthetic negative-binomial counts {cells} cells x {args.genes} genes, "
-                        f"n_var_clusters={args.clusters} (BASELINE.json config c3 at N=1; cells scale with N)",
+                        f"n_var_clusters={args.clusters} ({which})",
             "cells": cells, "genes": args.genes, "n_var_clusters": args.clusters,
-            "parallelism": f"genes sharded over {n_gpus} GPU(s)", "cache": "inputs (2 GB/GPU) larger than L2",
+            "parallelism": f"genes sharded over {n_gpus} GPU(s)", "cache": f"inputs ({cells * args.genes * 2 / n_gpus / 1e9:.1f} GB/GPU) larger than L2",
             "random_state": SEED}
 
 
@@ -219,8 +226,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
     counts = synth.counts(0, cells, g_lo, g_hi - g_lo)
     counts.comm = comm
     names = np.array([f"g{i}" for i in range(G)], dtype=object)
-    host_counts = torch.empty((cells, g_hi - g_lo), dtype=torch.int16).pin_memory()
-    host_counts.copy_(counts.data[:, :g_hi - g_lo])
+    host_counts = None
+    if not args.no_e2e:
+        host_counts = torch.empty((cells, g_hi - g_lo), dtype=torch.int16).pin_memory()
+        host_counts.copy_(counts.data[:, :g_hi - g_lo])
     torch.cuda.synchronize()
 
     def barrier():
@@ -295,19 +304,22 @@ def run_native(args, rank: int, world: int, local_rank: int):
                 "share_of_step": (tot.value / args.steps) / ms_per_step if ms_per_step else None}
 
     # end to end from pinned host counts through the public entry point
-    for _ in range(min(2, args.warmup)):
-        step_e2e()
-    _, e_dev_ms, e_wall_ms = timed(step_e2e, args.steps)
-    e_ms = max(e_dev_ms, e_wall_ms) / args.steps
-    h2d = int(host_counts.numel() * 2) * world
-    d2h = int(G * 50 * 4 + G * 4 + G * 4)
-    e2e = {"value": cells * G / (e_ms * 1e-3), "unit": "matrix-entries/s", "ms_per_step": e_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    if args.no_e2e:
+        e_ms, e2e = float("nan"), None
+    else:
+        for _ in range(min(2, args.warmup)):
+            step_e2e()
+        _, e_dev_ms, e_wall_ms = timed(step_e2e, args.steps)
+        e_ms = max(e_dev_ms, e_wall_ms) / args.steps
+        h2d = int(host_counts.numel() * 2) * world
+        d2h = int(G * 50 * 4 + G * 4 + G * 4)
+        e2e = {"value": cells * G / (e_ms * 1e-3), "unit": "matrix-entries/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     line = {
         "metric": "geneclust_fast_selection_throughput", "value": value, "unit": "matrix-entries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "end_to_end_selection_s": e_ms * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "end_to_end_selection_s": None if args.no_e2e else e_ms * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "selected_genes": int(len(sel)),
