@@ -62,7 +62,11 @@ __global__ void pairwise_combine_kernel(float *__restrict__ partial, int depth, 
 // out[j] = a[0, j] + a[1, j] + ... sequentially (numpy add.reduce over the outer axis of a C-ordered (C, m) array, m > 1)
 // one CTA per 32 columns; rows are staged through shared memory 64 at a time so the loads are coalesced and off the chain
 __global__ void __launch_bounds__(256)
-colsum_sequential_kernel(const float *__restrict__ a, int64_t C, int m, float *__restrict__ out) {
+colsum_sequential_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m,
+                         float *__restrict__ out0, float *__restrict__ out1) {
+    // blockIdx.y selects the array: the left and right halves of the deviance are summed by concurrent CTAs
+    const float *__restrict__ a = blockIdx.y == 0 ? a0 : a1;
+    float *__restrict__ out = blockIdx.y == 0 ? out0 : out1;
     __shared__ float tile[64][33];
     const int j0 = blockIdx.x * 32;
     const int tj = threadIdx.x & 31, ti = threadIdx.x >> 5;          // 8 row lanes x 32 columns
@@ -143,7 +147,7 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
     if (m == 1) {
         GC_CUDA(cudaMemcpyAsync(colsum, total, sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-        colsum_sequential_kernel<<<(unsigned)ceil_div(m, 32), 256, 0, st>>>(X, C, m, colsum);
+        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, 32), 1), 256, 0, st>>>(X, nullptr, C, m, colsum, nullptr);
         if (int rc = check_launch("colsum_sequential_kernel")) return rc;
     }
     deviance_terms_kernel<<<(unsigned)ceil_div<int64_t>(C, 128), 128, 0, st>>>(X, C, m, colsum, total, L, R);
@@ -156,9 +160,7 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
         // the second block wrote left[1]; move it to right[0]
         GC_CUDA(cudaMemcpyAsync(right, left + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-        colsum_sequential_kernel<<<(unsigned)ceil_div(m, 32), 256, 0, st>>>(L, C, m, left);
-        if (int rc = check_launch("colsum_sequential_kernel")) return rc;
-        colsum_sequential_kernel<<<(unsigned)ceil_div(m, 32), 256, 0, st>>>(R, C, m, right);
+        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, 32), 2), 256, 0, st>>>(L, R, C, m, left, right);
         if (int rc = check_launch("colsum_sequential_kernel")) return rc;
     }
     deviance_finish_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(left, right, m, out);
