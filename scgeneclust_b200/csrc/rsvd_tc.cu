@@ -295,11 +295,16 @@ tc_prep_kernel(const float *__restrict__ Q, int64_t n_k, int64_t n_k_pad, const 
         tpad[i] = i < G ? col_sum_f[i] * inv_total : 1.0f;
 }
 
-// colsum[0..63] = sum_k Q[k,:], colsum[64..127] = sum_k k_shift[k] Q[k,:]   (fixed block order => deterministic)
-__global__ void tc_colsum_kernel(const double *__restrict__ part, int n_blocks, float *__restrict__ colsum) {
+// colsum[0..63] = sum_k Q[k,:], colsum[64..127] = sum_k k_shift[k] Q[k,:]   (fixed order => deterministic):
+// 1024 threads = 128 outputs x 8 lanes; lane l adds blocks l, l+8, ... in order, the 8 lane sums are folded by a
+// fixed shuffle tree
+__global__ void __launch_bounds__(1024) tc_colsum_kernel(const double *__restrict__ part, int n_blocks, float *__restrict__ colsum) {
+    const int e = threadIdx.x >> 3, l = threadIdx.x & 7;
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += part[(int64_t)b * 128 + threadIdx.x];
-    colsum[threadIdx.x] = (float)s;
+    for (int b = l; b < n_blocks; b += 8) s += part[(int64_t)b * 128 + e];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
+    if (l == 0) colsum[e] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -649,7 +654,7 @@ extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float
                                                   M->row_sum_f, M->C, ceil128(M->C), M->col_sum_f, M->G, ceil128(M->ld),
                                                   1.0f / M->total, s.rpad, s.tpad);
     if (int rc = check_launch("tc_prep_kernel")) return rc;
-    tc_colsum_kernel<<<1, 128, 0, st>>>(s.colsum_part, s.prep_blocks, s.colsum);
+    tc_colsum_kernel<<<1, 1024, 0, st>>>(s.colsum_part, s.prep_blocks, s.colsum);
     if (int rc = check_launch("tc_colsum_kernel")) return rc;
 
     GC_REQUIRE(a.n_split <= 65535, "too many k slabs");

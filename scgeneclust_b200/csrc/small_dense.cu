@@ -9,40 +9,58 @@ constexpr int kN = 64;
 
 // Cholesky Gm = L L^T of the leading q x q block, then Rinv = (L^-1)^T as float32 (64 x 64, zero padded), so that
 // P @ Rinv has orthonormal columns when Gm = P^T P.  status[0] |= 1 on a non-positive pivot.
-__global__ void __launch_bounds__(kN)
+// 1024 threads = 64 rows x 16 lanes: the length-j dot product of every row is split over 16 lanes (k = lane, lane+16,
+// ...) and folded with shuffles in a fixed order, so a column costs ~4 dependent FMAs instead of up to 60.  Same for
+// the forward substitutions of the inverse (one column of L^-1 per 16-lane group).
+constexpr int kCholThreads = 1024;
+__global__ void __launch_bounds__(kCholThreads)
 chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, int32_t *status) {
     extern __shared__ double dyn_smem[];
     double (*L)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem);
     double (*Li)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem + kN * (kN + 1));
-    const int i = threadIdx.x;
-    for (int j = 0; j < kN; ++j) { L[i][j] = (i < q && j < q) ? Gm[i * kN + j] : 0.0; Li[i][j] = 0.0; }
+    __shared__ double rdiag[kN];                                   // 1 / L[j][j]
+    const int i = threadIdx.x >> 4, t = threadIdx.x & 15;          // row / column owner, lane inside its 16-group
+    for (int j = t; j < kN; j += 16) { L[i][j] = (i < q && j < q) ? Gm[i * kN + j] : 0.0; Li[i][j] = 0.0; }
     __syncthreads();
     for (int j = 0; j < q; ++j) {
         double s = 0.0;
         if (i >= j && i < q) {
-            s = L[i][j];
-            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+            for (int k = t; k < j; k += 16) s = fma(L[i][k], L[j][k], s);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+        __syncthreads();                                            // all reads of column j's inputs are done
+        if (t == 0 && i >= j && i < q) {
+            double v = L[i][j] - s;
+            if (i == j) {
+                if (!(v > 0.0)) { atomicOr(status, 1); v = 1.0; }
+                const double rs = rsqrt(v);                         // one reciprocal square root per column: the rows
+                rdiag[j] = rs;                                      // multiply by it instead of dividing by the pivot
+                L[j][j] = v * rs;
+            } else {
+                L[i][j] = v;
+            }
         }
         __syncthreads();
-        if (i == j) {
-            if (!(s > 0.0)) { atomicOr(status, 1); s = 1.0; }
-            L[j][j] = sqrt(s);
-        }
-        __syncthreads();
-        if (i > j && i < q) L[i][j] = s / L[j][j];
+        if (t == 0 && i > j && i < q) L[i][j] = L[i][j] * rdiag[j];
         __syncthreads();
     }
-    // inverse of the lower-triangular L: thread i solves column i of L X = I by forward substitution
+    // inverse of the lower-triangular L: the 16-lane group `i` solves column i of L X = I by forward substitution
+    // (two groups share a warp and run different trip counts: group-wide masks)
+    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
     if (i < q) {
         for (int r = i; r < q; ++r) {
-            double s = r == i ? 1.0 : 0.0;
-            for (int k = i; k < r; ++k) s -= L[r][k] * Li[k][i];
-            Li[r][i] = s / L[r][r];
+            double s = 0.0;
+            for (int k = i + t; k < r; k += 16) s = fma(L[r][k], Li[k][i], s);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, 16);
+            if (t == 0) Li[r][i] = ((r == i ? 1.0 : 0.0) - s) * rdiag[r];
+            __syncwarp(gmask);
         }
     }
     __syncthreads();
     // Rinv[a][b] = (L^-1)^T[a][b] = Li[b][a]
-    for (int j = 0; j < kN; ++j) Rinv[i * kN + j] = (i < q && j < q) ? (float)Li[j][i] : 0.f;
+    for (int j = t; j < kN; j += 16) Rinv[i * kN + j] = (i < q && j < q) ? (float)Li[j][i] : 0.f;
 }
 
 // Symmetric eigendecomposition of the leading q x q block of Gm by cyclic two-sided Jacobi with the round-robin
@@ -175,7 +193,7 @@ extern "C" int gc_chol_inv(const double *Gm, int q, float *Rinv, int32_t *status
         GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    chol_inv_kernel<<<1, kN, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
+    chol_inv_kernel<<<1, kCholThreads, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
     return check_launch("chol_inv_kernel");
 }
 
