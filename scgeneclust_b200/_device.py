@@ -265,13 +265,29 @@ class PanelAlgebra:
         self.rinv = torch.empty((Q_LD, Q_LD), dtype=torch.float32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
 
-    def chol_qr(self, P: torch.Tensor, q: int, out: torch.Tensor, comm=None) -> torch.Tensor:
-        """out = P @ R^-1 with P^T P = R^T R (one Cholesky-QR step).  With `comm` the rows of P are sharded and
-        the Gram matrix is all-reduced."""
+    def gram_of(self, P: torch.Tensor, comm=None, replicated: bool = False) -> torch.Tensor:
+        """self.gram = P^T P in float64.  `comm` + rows sharded (gene-space panels): local Gram, all-reduced.
+        `comm` + `replicated` (cell-space panels, identical on every rank after their all-reduce): every rank takes
+        the Gram of its own slice of the rows and the slices are all-reduced - the panel has as many rows as there
+        are cells, so the replicated version made every rank pay C x 64 x 64 float64 FMAs per normalisation."""
         L, st = lib(), stream_handle()
+        if comm is not None and replicated and comm.world > 1:
+            lo, hi = comm.split_range(P.shape[0])
+            if hi > lo:
+                L.panel_gram(ptr(P[lo:hi]), hi - lo, ptr(self.gram), ptr(self.scratch), st)
+            else:
+                self.gram.zero_()
+            comm.all_reduce_sum(self.gram)
+            return self.gram
         L.panel_gram(ptr(P), P.shape[0], ptr(self.gram), ptr(self.scratch), st)
         if comm is not None:
             comm.all_reduce_sum(self.gram)
+        return self.gram
+
+    def chol_qr(self, P: torch.Tensor, q: int, out: torch.Tensor, comm=None, replicated: bool = False) -> torch.Tensor:
+        """out = P @ R^-1 with P^T P = R^T R (one Cholesky-QR step); `comm` / `replicated` as in `gram_of`."""
+        L, st = lib(), stream_handle()
+        self.gram_of(P, comm, replicated)
         L.chol_inv(ptr(self.gram), q, ptr(self.rinv), ptr(self.status), st)
         L.panel_matmul(ptr(P), P.shape[0], ptr(self.rinv), ptr(out), st)
         return out
@@ -396,7 +412,8 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     def normalise(trans, Y):
         # rows of Y: cells (replicated across shards) for trans=0, local genes for trans=1
         dst = buf_c if trans == 0 else buf_g
-        return alg.chol_qr(Y, q, dst, comm if (comm is not None and trans == 1) else None)
+        # trans == 1: rows = this rank's genes (sharded); trans == 0: rows = all cells, replicated after the all-reduce
+        return alg.chol_qr(Y, q, dst, comm, replicated=(trans == 0))
 
     Qcur = Qp
     for _ in range(n_iter):
@@ -404,15 +421,12 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         Qcur = normalise(bwd, apply(bwd, Qcur))
     # final range: orthonormal basis by two Cholesky-QR steps (qr_normalizer of extmath.py:386)
     Y = apply(fwd, Qcur)
-    sh = comm if (comm is not None and fwd == 1) else None
-    Q1 = alg.chol_qr(Y, q, buf_c if fwd == 0 else buf_g, sh)
-    Qf = alg.chol_qr(Q1, q, Y, sh)                       # second pass writes into the tmp buffer
+    Q1 = alg.chol_qr(Y, q, buf_c if fwd == 0 else buf_g, comm, replicated=(fwd == 0))
+    Qf = alg.chol_qr(Q1, q, Y, comm, replicated=(fwd == 0))      # second pass writes into the tmp buffer
     Qf = Qf.clone()
     Bt = apply(bwd, Qf)                                  # B^T = A^T Q  (A.shape[1] x q)
     # thin SVD of B through the q x q eigenproblem  B B^T = Uhat S^2 Uhat^T  (float64, on the device)
-    L.panel_gram(ptr(Bt), Bt.shape[0], ptr(alg.gram), ptr(alg.scratch), st)
-    if comm is not None and bwd == 1:
-        comm.all_reduce_sum(alg.gram)
+    alg.gram_of(Bt, comm, replicated=(bwd == 0))
     evals = torch.empty(Q_LD, dtype=torch.float64, device=dev)
     uhat = torch.empty((Q_LD, Q_LD), dtype=torch.float32, device=dev)
     L.sym_eig(ptr(alg.gram), q, ptr(evals), ptr(uhat), None, st)
