@@ -266,10 +266,10 @@ kpp_trial_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d, con
 }
 
 // One greedy round as ONE kernel: every CTA computes its trial-distance tile (as kpp_trial_kernel); the LAST CTA to
-// finish (atomic ticket) then runs the tail of the round that used to be two more launches: candidates_pot = fixed-order
-// sum of the partials, first argmin, new current_pot (kpp_choose_kernel) and - unless this was the last round - the head
-// of the next one (kpp_pick_kernel): adopt the winner's distances, sequential float32 cumsum staged through shared
-// memory, searchsorted of the next uniforms inside shared memory.  Arithmetic and summation orders are unchanged.
+// finish (atomic ticket) then runs the tail of the round: candidates_pot = fixed-order sum of the partials, first
+// argmin, new current_pot and - unless this was the last round - the head of the next one (what kpp_pick_kernel does
+// for round 1): adopt the winner's distances, sequential float32 cumsum staged through shared memory, searchsorted of
+// the next uniforms inside shared memory.
 constexpr int kRoundChunk = 6144;     // floats of cumsum staged per pass of the tail (24 KB)
 __global__ void __launch_bounds__(kKppThreads)
 kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t n, int d, int32_t *cand,
@@ -427,22 +427,6 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t
     }
 }
 
-// round step C (1 warp): candidates_pot = sum of partials (fixed order), first argmin, new current_pot
-__global__ void kpp_choose_kernel(KppState *st, const double *__restrict__ partial, int n_blocks, int n_trials) {
-    if (threadIdx.x == 0) {
-        float best_pot = 0.f;
-        int best = 0;
-        for (int c = 0; c < n_trials; ++c) {
-            double s = 0.0;
-            for (int b = 0; b < n_blocks; ++b) s += partial[(int64_t)c * n_blocks + b];
-            const float pot = (float)s;
-            if (c == 0 || pot < best_pot) { best_pot = pot; best = c; }
-        }
-        st->current_pot = best_pot;
-        st->best = best;
-    }
-}
-
 // first centre: closest = dist(X[first]), current_pot = sum
 __global__ void kpp_first_kernel(KppState *st, const double *__restrict__ partial, int n_blocks,
                                  int32_t *__restrict__ cand, int32_t first, int32_t *__restrict__ indices_out) {
@@ -457,11 +441,6 @@ __global__ void kpp_first_kernel(KppState *st, const double *__restrict__ partia
 }
 
 __global__ void kpp_set_cand_kernel(int32_t *cand, int32_t first) { cand[0] = first; }
-
-__global__ void kpp_finish_kernel(const KppState *st, const int32_t *__restrict__ cand,
-                                  int32_t *__restrict__ indices_out, int K) {
-    if (threadIdx.x == 0) indices_out[K - 1] = cand[st->best];
-}
 
 __global__ void gather_rows_kernel(const float *__restrict__ X, int64_t ldx, const int32_t *__restrict__ idx,
                                    int n_rows, int d, float *__restrict__ out) {

@@ -50,18 +50,6 @@ def _singleton_deviances(adata, mask: np.ndarray) -> np.ndarray:
     return compute_deviance(np.asarray(adata.X)[:, mask])
 
 
-def _residual_columns(adata, mask: np.ndarray) -> np.ndarray:
-    """Pearson-residual columns of the masked genes as a host float32 (cells x n_masked) array."""
-    st = get_state(adata)
-    if st.Z is not None:
-        import torch
-        idx = torch.from_numpy(np.flatnonzero(mask)).to(st.Z.device)
-        return st.Z.index_select(1, idx).cpu().numpy()
-    if st.op is not None:
-        return st.op.materialize_columns(np.flatnonzero(mask)).cpu().numpy()
-    return np.asarray(adata.X)[:, mask]
-
-
 _RAND_R_MAX = 2147483647
 _EULER_GAMMA = float(np.euler_gamma)
 
