@@ -190,3 +190,66 @@ def test_hdbscan_tail_labels_equal_sklearn_fork():
         assert scores.shape == (n,) and (scores >= 0).all() and (scores <= 1).all()
     with __import__('pytest').raises(ValueError):
         mst_to_clusters(edges[:-1], n)                                        # spanning forest: the reference fails too
+
+
+def test_device_matrix_stands_in_for_adata_x():
+    """`DeviceMatrix` (adata.X / varp['redundancy'] kept on the device until read) behaves like the ndarray it replaces
+    for everything the stage functions do with it: shape / dtype, column and row subsetting through AnnDataLite's
+    in-place subset calls, np.asarray, copy.  Runs on a CPU tensor: the class is device-agnostic."""
+    import numpy as np
+    import torch
+    from scgeneclust_b200._anndata_lite import AnnDataLite, DeviceMatrix
+    rs = np.random.RandomState(0)
+    A = rs.standard_normal((7, 5)).astype(np.float32)
+    dm = DeviceMatrix(torch.from_numpy(A.copy()))
+    assert dm.shape == (7, 5) and dm.dtype == np.float32 and dm.ndim == 2
+    assert np.array_equal(np.asarray(dm), A)
+    ad = AnnDataLite(dm, var_names=[f"g{i}" for i in range(5)], obs_names=[f"c{i}" for i in range(7)])
+    keep_cells = np.array([True, False, True, True, False, True, True])
+    ad._inplace_subset_obs(keep_cells)
+    assert isinstance(ad.X, DeviceMatrix) and ad.X.shape == (5, 5) and list(ad.obs_names) == ["c0", "c2", "c3", "c5", "c6"]
+    ad._inplace_subset_var(np.array(["g3", "g1"], dtype=object))
+    assert isinstance(ad.X, DeviceMatrix) and np.array_equal(np.asarray(ad.X), A[keep_cells][:, [3, 1]])
+    cp = ad.copy()
+    cp.X.tensor.zero_()
+    assert np.asarray(ad.X).any()                                      # copy is deep
+    assert np.array_equal(dm[[0, 2], :].tensor.numpy(), A[[0, 2]])     # integer row lists
+    assert np.array_equal(np.asarray(dm)[1:3, 2], dm[1:3, 2])          # anything else falls back to a host array
+    d64 = DeviceMatrix(torch.zeros((3, 3), dtype=torch.float64))
+    assert d64.dtype == np.float64
+
+
+def test_anndata_lite_lazy_default_names():
+    import numpy as np
+    from scgeneclust_b200._anndata_lite import AnnDataLite
+    ad = AnnDataLite(np.zeros((3, 4), np.float32))
+    assert list(ad.var_names) == ["gene_0", "gene_1", "gene_2", "gene_3"] and list(ad.obs_names) == ["cell_0", "cell_1", "cell_2"]
+    ad._inplace_subset_var(np.array([True, False, True, False]))
+    assert list(ad.var_names) == ["gene_0", "gene_2"] and ad.shape == (3, 2)
+
+
+def test_glosh_scores_and_noise_labels_on_separated_blobs():
+    """GLOSH outlier scores from the condensed tree (scGeneClust/tl/cluster.py:131): two tight blobs become two
+    clusters, the point that joins a blob at a much larger distance than the blob's own scale gets the top outlier
+    score, points leaving the root are noise (-1); labels equal scikit-learn's fork on the same tree."""
+    import numpy as np
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    from sklearn.cluster._hdbscan import _linkage, _tree
+    from scgeneclust_b200.tl._hdbscan_tail import mst_to_clusters
+    rs = np.random.RandomState(3)
+    blobs = np.concatenate([rs.normal(0, 0.05, size=(40, 2)), rs.normal(5, 0.05, size=(40, 2))])
+    strays = np.array([[2.5, 2.5], [2.4, -3.0], [8.0, 0.0]])
+    pts = np.concatenate([blobs, strays])
+    dmat = np.linalg.norm(pts[:, None] - pts[None], axis=2)
+    mst = minimum_spanning_tree(dmat).tocoo()
+    edges = np.stack([mst.row, mst.col, mst.data], axis=1)
+    edges = edges[np.argsort(edges[:, 2])]
+    labels, scores = mst_to_clusters(edges, len(pts), min_cluster_size=3)
+    assert set(labels[:40]) == {labels[0]} and set(labels[40:80]) == {labels[40]} and labels[0] != labels[40]
+    assert (labels[81:] == -1).all()
+    assert int(np.argmax(scores)) == 80 and scores[80] > 0.9          # joins blob 1 at ~3.5 against a blob scale of ~0.05
+    assert np.median(scores[:80]) < 0.1
+    assert scores.min() >= 0 and scores.max() <= 1
+    rec = np.zeros(len(pts) - 1, dtype=_linkage.MST_edge_dtype)
+    rec['current_node'], rec['next_node'], rec['distance'] = edges[:, 0].astype(np.intp), edges[:, 1].astype(np.intp), edges[:, 2]
+    assert np.array_equal(labels, _tree.tree_to_labels(_linkage.make_single_linkage(rec), 3, "eom", False, 0.0, None)[0])
