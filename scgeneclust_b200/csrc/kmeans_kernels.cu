@@ -265,6 +265,34 @@ kpp_trial_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d, con
     if (threadIdx.x == 0) partial[(int64_t)c * gridDim.x + blockIdx.x] = red[0];
 }
 
+// Once per k-means++ call: Xt[f][i] = (double)X[i][f] (feature-major, so a warp reads consecutive samples) and
+// yy[i] = sum_f fma(y_f, y_f, .) in the order of sqdist_upcast.  The round kernel then spends 50 DFMAs per
+// (candidate, sample) instead of 100 DFMAs + 100 float->double conversions; the distances are bit-identical.
+__global__ void kpp_prep_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d, double *__restrict__ Xt,
+                                double *__restrict__ yy) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *y = X + i * ldx;
+    double s = 0.0;
+    for (int f = 0; f < d; ++f) {
+        const double yv = (double)y[f];
+        Xt[(int64_t)f * n + i] = yv;
+        s = fma(yv, yv, s);
+    }
+    yy[i] = s;
+}
+// same value as sqdist_upcast(xc, xx, X + i*ldx, d), from the prepared arrays
+__device__ __forceinline__ float sqdist_prepared(const float *__restrict__ xc, double xx, const double *__restrict__ Xt,
+                                                 const double *__restrict__ yy, int64_t n, int64_t i, int d) {
+    double dot = 0.0;
+    for (int f = 0; f < d; ++f) dot = fma((double)xc[f], Xt[(int64_t)f * n + i], dot);
+    double v = -2.0 * dot;
+    v = v + xx;
+    v = v + yy[i];
+    const float r = (float)v;
+    return r > 0.f ? r : 0.f;
+}
+
 // One greedy round as ONE kernel: every CTA computes its trial-distance tile (as kpp_trial_kernel); the LAST CTA to
 // finish (atomic ticket) then runs the tail of the round: candidates_pot = fixed-order sum of the partials, first
 // argmin, new current_pot and - unless this was the last round - the head of the next one (what kpp_pick_kernel does
@@ -272,7 +300,8 @@ kpp_trial_kernel(const float *__restrict__ X, int64_t ldx, int64_t n, int d, con
 // the next uniforms inside shared memory.
 constexpr int kRoundChunk = 6144;     // floats of cumsum staged per pass of the tail (24 KB)
 __global__ void __launch_bounds__(kKppThreads)
-kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t n, int d, int32_t *cand,
+kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
+                 const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
                  float *closest, float *trial_dist, double *partial, const double *__restrict__ uniforms, int n_trials,
                  int32_t *__restrict__ indices_out, int round, int last_round, unsigned int *ticket) {
     __shared__ float sc[kDMax];
@@ -298,7 +327,7 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, int64_t
         const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         double v = 0.0;
         if (i < n) {
-            const float dd = fminf(closest[i], sqdist_upcast(sc, sxx, X + i * ldx, d));
+            const float dd = fminf(closest[i], sqdist_prepared(sc, sxx, Xt, yy, n, i, d));
             trial_dist[(int64_t)c * n + i] = dd;
             v = (double)dd;
         }
@@ -604,7 +633,8 @@ extern "C" int64_t gc_kmeanspp_scratch_bytes(int64_t n, int n_trials) {
     const int64_t n_blocks = ceil_div<int64_t>(n, kKppThreads);
     // state | cand[n_trials] | closest[n] | cumsum[n] | trial_dist[n_trials*n] | partial[n_trials*n_blocks]
     return 256 + 256 + (int64_t)sizeof(float) * (2 * n + (int64_t)n_trials * n) + 256 * 3 +
-           (int64_t)sizeof(double) * n_trials * n_blocks + 256 + 256 /* ticket */;
+           (int64_t)sizeof(double) * n_trials * n_blocks + 256 + 256 /* ticket */ +
+           (int64_t)sizeof(double) * (n * (kDMax + 1)) + 512 /* feature-major float64 copy + squared norms */;
 }
 
 extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, int K, int32_t first_center,
@@ -640,13 +670,17 @@ extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, i
     }
     unsigned int *ticket = (unsigned int *)align((char *)(partial + (int64_t)n_trials * n_blocks));
     GC_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+    double *Xt = (double *)align((char *)(ticket + 64));
+    double *yy = (double *)align((char *)(Xt + (int64_t)d * n));
+    kpp_prep_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, st>>>(X, ldx, n, d, Xt, yy);
+    if (int rc = check_launch("kpp_prep_kernel")) return rc;
     if (K > 1) {
         // head of round 1 (no winner to adopt yet), then one launch per round
         kpp_pick_kernel<<<1, 1024, 0, st>>>(state, closest, trial, n, uniforms, n_trials, cand, cumsum, indices_out, 1);
         if (int rc = check_launch("kpp_pick_kernel")) return rc;
         dim3 grid((unsigned)n_blocks, (unsigned)n_trials);
         for (int round = 1; round < K; ++round) {
-            kpp_round_kernel<<<grid, kKppThreads, 0, st>>>(state, X, ldx, n, d, cand, closest, trial, partial, uniforms,
+            kpp_round_kernel<<<grid, kKppThreads, 0, st>>>(state, X, ldx, Xt, yy, n, d, cand, closest, trial, partial, uniforms,
                                                            n_trials, indices_out, round, round == K - 1 ? 1 : 0, ticket);
             if (int rc = check_launch("kpp_round_kernel")) return rc;
         }
