@@ -53,7 +53,7 @@ def parse():
 # clocks / throttle sampling during the timed region
 # -------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.02):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
