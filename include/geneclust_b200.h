@@ -226,6 +226,15 @@ int gc_mi_cd(const double *XR, int64_t ldr, int64_t G, int n, const int32_t *lab
 int64_t gc_mst_scratch_bytes(int64_t N);
 int gc_mst_boruvka(const double *R, int64_t N, int32_t *edges_out, int32_t *n_edges_out, void *scratch, void *stream);
 
+/* HOST function (all pointers are host memory, no GPU work): the HDBSCAN tail of GeneClust-ps
+ * (scGeneClust/tl/cluster.py:127-130: hdbscan label -> condense_tree(., min_cluster_size) -> compute_stability ->
+ * get_clusters('eom', allow_single_cluster=False) labelling).  mst_sorted_host: n_edges x 3 (i, j, weight), ascending by
+ * weight, n_edges + 1 points.  Outputs: the condensed tree (parent/child/lambda/size, capacity 2 * n_edges rows,
+ * n_rows_host[0] rows written - the input of the GLOSH scores) and labels_host[n_edges + 1] (-1 = noise). */
+int gc_host_hdbscan_tree(const double *mst_sorted_host, int64_t n_edges, int64_t min_cluster_size, int64_t *parent_host,
+                         int64_t *child_host, double *lambda_host, int64_t *size_host, int64_t *n_rows_host,
+                         int64_t *labels_host);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Synthetic negative-binomial counts (bench/test harness): counter-based, bit-identical
  * to oracle/synth.py.  Writes rows [c0, c0+nc) x genes [g0, g0+ng) of the global matrix into counts[nc x ld].

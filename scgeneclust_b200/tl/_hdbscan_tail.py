@@ -171,14 +171,38 @@ def outlier_scores(tree: np.ndarray) -> np.ndarray:
     return result
 
 
-def mst_to_clusters(mst_sorted: np.ndarray, n_vars: int, min_cluster_size: int = 3):
+def native_tree_and_labels(mst_sorted: np.ndarray, min_cluster_size: int = 3):
+    """Condensed tree + EOM labels from the C++ host routine `gc_host_hdbscan_tree` of libgeneclust_b200.so (the same
+    algorithm as `single_linkage_label` / `condense_tree` / `compute_stability` / `get_clusters_eom` above, ~30x
+    faster than the Python loops; tests compare the two)."""
+    from .._lib import lib
+    mst = np.ascontiguousarray(mst_sorted, dtype=np.float64)
+    n_edges = mst.shape[0]
+    parent = np.empty(2 * n_edges, dtype=np.int64)
+    child = np.empty(2 * n_edges, dtype=np.int64)
+    lam = np.empty(2 * n_edges, dtype=np.float64)
+    size = np.empty(2 * n_edges, dtype=np.int64)
+    n_rows = np.zeros(1, dtype=np.int64)
+    labels = np.empty(n_edges + 1, dtype=np.int64)
+    lib().host_hdbscan_tree(mst.ctypes.data, n_edges, int(min_cluster_size), parent.ctypes.data, child.ctypes.data,
+                            lam.ctypes.data, size.ctypes.data, n_rows.ctypes.data, labels.ctypes.data)
+    k = int(n_rows[0])
+    tree = np.empty(k, dtype=CONDENSED_DTYPE)
+    tree['parent'], tree['child'], tree['lambda_val'], tree['child_size'] = parent[:k], child[:k], lam[:k], size[:k]
+    return tree, labels.astype(np.intp)
+
+
+def mst_to_clusters(mst_sorted: np.ndarray, n_vars: int, min_cluster_size: int = 3, native: bool = True):
     """The five calls of scGeneClust/tl/cluster.py:127-131 -> (labels, outlier_scores)."""
     if mst_sorted.shape[0] + 1 != n_vars:
         # the reference feeds a spanning FOREST to `label`, which assumes N - 1 edges, and then fails when it assigns
         # the mis-sized result to adata.var (SURVEY.md section 7, "MST graph is not complete")
         raise ValueError(f"the MI > 0 redundancy graph is disconnected: {mst_sorted.shape[0]} MST edges for {n_vars} "
                          "genes (the reference fails here as well: Length of values does not match length of index)")
-    slt = single_linkage_label(mst_sorted)
-    tree = condense_tree(slt, min_cluster_size)
-    labels = get_clusters_eom(tree, compute_stability(tree))
+    if native:
+        tree, labels = native_tree_and_labels(mst_sorted, min_cluster_size)
+    else:
+        slt = single_linkage_label(mst_sorted)
+        tree = condense_tree(slt, min_cluster_size)
+        labels = get_clusters_eom(tree, compute_stability(tree))
     return labels, outlier_scores(tree)

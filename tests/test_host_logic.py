@@ -180,6 +180,12 @@ def test_hdbscan_tail_labels_equal_sklearn_fork():
         edges = np.stack([mst.row, mst.col, mst.data], axis=1)
         edges = edges[np.argsort(edges[:, 2])]
         labels, scores = mst_to_clusters(edges, n, min_cluster_size=3)
+        labels_py, scores_py = mst_to_clusters(edges, n, min_cluster_size=3, native=False)    # Python restatement
+        assert np.array_equal(labels, labels_py) and np.array_equal(scores, scores_py)
+        from scgeneclust_b200.tl._hdbscan_tail import condense_tree, native_tree_and_labels
+        tree_c, _ = native_tree_and_labels(edges, 3)
+        tree_py = condense_tree(single_linkage_label(edges), 3)
+        assert all(np.array_equal(tree_c[f], tree_py[f]) for f in ('parent', 'child', 'lambda_val', 'child_size'))
         rec = np.zeros(n - 1, dtype=_linkage.MST_edge_dtype)
         rec['current_node'], rec['next_node'], rec['distance'] = edges[:, 0].astype(np.intp), edges[:, 1].astype(np.intp), edges[:, 2]
         slt = _linkage.make_single_linkage(rec)
