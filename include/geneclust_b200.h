@@ -235,6 +235,13 @@ int gc_host_hdbscan_tree(const double *mst_sorted_host, int64_t n_edges, int64_t
                          int64_t *child_host, double *lambda_host, int64_t *size_host, int64_t *n_rows_host,
                          int64_t *labels_host);
 
+/* HOST function: summed isolation depths of sklearn IsolationForest(random_state=seed).fit(x.reshape(-1, 1)) for
+ * n <= 256 one-dimensional float32 samples - the singleton-rescue outlier test of scGeneClust/tl/selection.py:51
+ * (numpy MT19937 seeding chain, sklearn's xorshift rand_r, depth-first random splits; see tl/selection.py).
+ * c_of_host[m] = _average_path_length(m), m = 0..n (from the caller, so its log is numpy's); depths_host[n]. */
+int gc_host_iforest_depths(const float *x_host, int n, uint32_t seed, int n_estimators, const double *c_of_host,
+                           double *depths_host);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Synthetic negative-binomial counts (bench/test harness): counter-based, bit-identical
  * to oracle/synth.py.  Writes rows [c0, c0+nc) x genes [g0, g0+ng) of the global matrix into counts[nc x ld].

@@ -174,3 +174,119 @@ extern "C" int gc_host_hdbscan_tree(const double *mst_sorted, int64_t n_edges, i
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Singleton rescue: summed isolation depths of sklearn's IsolationForest(random_state=seed) on n <= 256 one-dimensional
+// float32 samples (scGeneClust/tl/selection.py:51), the restatement documented in tl/selection.py::_isolation_forest_1d:
+// numpy legacy MT19937 seeding chain -> sklearn's xorshift rand_r -> depth-first random splits, left child first.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Mt19937 {
+    uint32_t mt[624];
+    int idx;
+    explicit Mt19937(uint32_t seed) {                                  // init_genrand (numpy _legacy_seeding for an int seed)
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    // RandomState.randint(2**31 - 1): masked rejection on 32-bit words (range 2**31 - 2, mask 0x7fffffff)
+    uint32_t randint31() {
+        uint32_t v;
+        do { v = next() & 0x7fffffffu; } while (v > 0x7ffffffeu);
+        return v;
+    }
+    double random_sample() {                                           // rk_double
+        const uint32_t a = next() >> 5, b = next() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+};
+
+inline uint32_t rand_r_step(uint32_t &s) {                             // sklearn utils/_random.pxd our_rand_r
+    if (s == 0) s = 1;
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    return s & 0x7fffffffu;
+}
+
+}  // namespace
+
+// depths_host[i] = sum over the trees of (node depth + c_of[leaf size]); c_of_host[m] = sklearn's _average_path_length(m),
+// m = 0..n, computed by the caller with numpy so that its log() is numpy's.
+extern "C" int gc_host_iforest_depths(const float *x_host, int n, uint32_t seed, int n_estimators, const double *c_of_host,
+                                      double *depths_host) {
+    GC_REQUIRE(x_host && c_of_host && depths_host, "null pointer");
+    GC_REQUIRE(n >= 1 && n <= 256 && n_estimators >= 1, "n must be in [1, 256] (max_samples='auto' keeps every sample)");
+    std::vector<double> y(n);
+    {
+        Mt19937 r(seed);                                               // y = RandomState(seed).uniform(size=n): impurity only
+        for (int i = 0; i < n; ++i) y[i] = r.random_sample();
+    }
+    std::vector<uint32_t> seeds(n_estimators);
+    {
+        Mt19937 r(seed);                                               // BaseBagging._fit: randint(MAX_INT, size=n_estimators)
+        for (int t = 0; t < n_estimators; ++t) seeds[t] = r.randint31();
+    }
+    int max_depth = 0;
+    while ((1 << max_depth) < std::max(n, 2)) ++max_depth;             // ceil(log2(max(n, 2)))
+    const double eps = std::numeric_limits<double>::epsilon();
+    for (int i = 0; i < n; ++i) depths_host[i] = 0.0;
+    std::vector<double> contrib(n);
+    struct Node { std::vector<int> ids; int depth; };
+    std::vector<Node> stack;
+    for (int t = 0; t < n_estimators; ++t) {
+        const uint32_t tree_seed = Mt19937(seeds[t]).randint31();      // _set_random_states
+        uint32_t state = Mt19937(tree_seed).randint31();               // Splitter.__cinit__: randint(0, RAND_R_MAX)
+        stack.clear();
+        Node root;
+        root.ids.resize(n);
+        for (int i = 0; i < n; ++i) root.ids[i] = i;
+        root.depth = 0;
+        stack.push_back(std::move(root));
+        while (!stack.empty()) {
+            Node node = std::move(stack.back());
+            stack.pop_back();
+            const int m = (int)node.ids.size();
+            bool leaf = node.depth >= max_depth || m < 2;
+            if (!leaf) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int i : node.ids) { s1 += y[i]; s2 += y[i] * y[i]; }
+                const double mean = s1 / m;
+                leaf = s2 / m - mean * mean <= eps;
+            }
+            if (!leaf) {
+                rand_r_step(state);                                    // rand_int(0, 1): the only feature is drawn
+                float lo = x_host[node.ids[0]], hi = lo;
+                for (int i : node.ids) { const float v = x_host[i]; if (v < lo) lo = v; else if (v > hi) hi = v; }
+                if (hi <= lo + 1e-7f) {                                // FEATURE_THRESHOLD, float32 arithmetic
+                    leaf = true;
+                } else {
+                    double thr = ((double)hi - (double)lo) * (double)rand_r_step(state) / 2147483647.0 + (double)lo;
+                    if (thr == (double)hi) thr = (double)lo;
+                    Node left, right;
+                    left.depth = right.depth = node.depth + 1;
+                    for (int i : node.ids) ((double)x_host[i] <= thr ? left : right).ids.push_back(i);
+                    stack.push_back(std::move(right));                 // left child is built first
+                    stack.push_back(std::move(left));
+                }
+            }
+            if (leaf) {
+                const double d = (double)(node.depth + 1) + c_of_host[m] - 1.0;
+                for (int i : node.ids) contrib[i] = d;
+            }
+        }
+        for (int i = 0; i < n; ++i) depths_host[i] += contrib[i];
+    }
+    return 0;
+}

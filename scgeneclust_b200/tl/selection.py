@@ -178,6 +178,24 @@ def _isolation_forest_1d(values: np.ndarray, random_state: int, n_estimators: in
     return scores - (-0.5) < 0
 
 
+def _isolation_forest_1d_native(values: np.ndarray, random_state: int, n_estimators: int = 100,
+                                return_scores: bool = False) -> np.ndarray:
+    """The same restatement as `_isolation_forest_1d`, with the forest built by the C++ host routine
+    `gc_host_iforest_depths` of libgeneclust_b200.so (n <= 256 samples, seeds < 2**32); the path-length table and the
+    final score formula stay in numpy so that every transcendental is numpy's."""
+    from .._lib import lib
+    x32 = np.ascontiguousarray(np.asarray(values, dtype=np.float64).astype(np.float32))
+    n = x32.shape[0]
+    c_of = np.array([_avg_path_length(m) for m in range(n + 1)], dtype=np.float64)
+    depths = np.empty(n, dtype=np.float64)
+    lib().host_iforest_depths(x32.ctypes.data, n, int(random_state), n_estimators, c_of.ctypes.data, depths.ctypes.data)
+    denominator = n_estimators * c_of[n]
+    scores = -(2 ** (-np.divide(depths, denominator, out=np.ones_like(depths), where=denominator != 0)))
+    if return_scores:
+        return scores
+    return scores - (-0.5) < 0
+
+
 def _isolation_forest_outliers(values: np.ndarray, random_state: int) -> np.ndarray:
     """`IsolationForest(random_state=...).fit_predict(values.reshape(-1, 1)) == -1` (scGeneClust/tl/selection.py:51).
 
@@ -185,14 +203,15 @@ def _isolation_forest_outliers(values: np.ndarray, random_state: int) -> np.ndar
     holds all samples; for n = 1 the normaliser c(1) = 0 makes every score exactly -0.5, for n = 2 every tree isolates
     both samples at depth 1 (or keeps two equal values in one leaf, path length c(2) = 1) and every score is
     -2^(-1) = -0.5 as well; `offset_` is -0.5, the decision function is 0 and `predict` flags only values < 0: no
-    outlier.  Up to 64 finite values use the line-by-line restatement above; anything else (more values, NaN / inf,
+    outlier.  Up to 256 finite values (sklearn's max_samples: every tree still sees every sample) use the line-by-line
+    restatement above in its native form; anything else (more values, NaN / inf,
     which make sklearn take its missing-value path or raise) goes through sklearn itself."""
     n = values.shape[0]
     finite = bool(np.isfinite(values).all())
     if n <= 2 and not np.isinf(values).any():
         return np.zeros(n, dtype=bool)
-    if n <= 64 and finite and bool(np.isfinite(values.astype(np.float32)).all()):
-        return _isolation_forest_1d(values, random_state)
+    if n <= 256 and finite and bool(np.isfinite(values.astype(np.float32)).all()) and 0 <= random_state < 2 ** 32:
+        return _isolation_forest_1d_native(values, random_state)
     return IsolationForest(random_state=random_state).fit_predict(values.reshape(-1, 1)) == -1
 
 

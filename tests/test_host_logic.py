@@ -136,7 +136,8 @@ def test_isolation_forest_restatement_equals_sklearn():
     1-D IsolationForest; its score_samples must be bit-identical to sklearn's own, incl. ties / near-constant data."""
     import numpy as np
     from sklearn.ensemble import IsolationForest
-    from scgeneclust_b200.tl.selection import _first_randint31, _isolation_forest_1d, _isolation_forest_outliers
+    from scgeneclust_b200.tl.selection import (_first_randint31, _isolation_forest_1d, _isolation_forest_1d_native,
+                                                _isolation_forest_outliers)
     sd = np.array([0, 1, 5, 123456, 2 ** 31 - 2, 99999999])
     assert np.array_equal(_first_randint31(sd), [np.random.RandomState(int(s)).randint(2 ** 31 - 1) for s in sd])
     rs = np.random.RandomState(2)
@@ -154,8 +155,14 @@ def test_isolation_forest_restatement_equals_sklearn():
         else:
             v = np.concatenate([np.full(n - 2, 3.25), rs.normal(size=2) * 1e-8 + 3.25])   # constant in float32
         forest = IsolationForest(random_state=seed).fit(v.reshape(-1, 1))
-        assert np.array_equal(_isolation_forest_1d(v, seed, return_scores=True), forest.score_samples(v.reshape(-1, 1)))
+        ref_scores = forest.score_samples(v.reshape(-1, 1))
+        assert np.array_equal(_isolation_forest_1d(v, seed, return_scores=True), ref_scores)            # Python restatement
+        assert np.array_equal(_isolation_forest_1d_native(v, seed, return_scores=True), ref_scores)     # C++ host routine
         assert np.array_equal(_isolation_forest_outliers(v, seed), forest.predict(v.reshape(-1, 1)) == -1)
+    for n in (150, 256):                                                     # up to sklearn's max_samples: still every sample per tree
+        v = rs.standard_normal(n) * 50
+        forest = IsolationForest(random_state=7).fit(v.reshape(-1, 1))
+        assert np.array_equal(_isolation_forest_1d_native(v, 7, return_scores=True), forest.score_samples(v.reshape(-1, 1)))
     for n in (1, 2):                                                         # closed-form small cases
         v = rs.normal(size=n)
         assert np.array_equal(_isolation_forest_outliers(v, 0),
