@@ -331,6 +331,35 @@ def pca_solver(n_samples: int, n_features: int, n_comps: int) -> str:
     return "full"
 
 
+def _small_pca(op: ResidualOperator, samples: str, solver: str, n_comps: int) -> torch.Tensor:
+    """The two exact solvers sklearn's 'auto' policy picks for SMALL inputs (decomposition/_pca.py:524-536, :540-700):
+    'covariance_eigh' (<= 1000 features and >= 10x more samples, e.g. gene PCA of a data set with a few hundred cells)
+    and 'full' (both dimensions <= 500, or n_comps >= 0.8 min_dim).  These sizes are far from the hot path: the residual
+    matrix is materialised and the dense factorisations are library calls (torch.linalg on the device, float64), followed
+    by sklearn's v-based sign flip and its transform formulas.  Returns float32 scores (n_samples x n_comps)."""
+    Z = op.materialize().to(torch.float64)
+    X = Z.t().contiguous() if samples == "genes" else Z
+    n = X.shape[0]
+    mean = X.mean(dim=0)
+    if solver == "covariance_eigh":
+        Cm = X.t() @ X
+        Cm -= n * torch.outer(mean, mean)
+        Cm /= (n - 1)
+        evals, evecs = torch.linalg.eigh(Cm)                      # ascending
+        Vt = evecs.t().flip(0)[:n_comps].contiguous()
+        idx = Vt.abs().argmax(dim=1)
+        Vt *= torch.sign(Vt[torch.arange(Vt.shape[0], device=Vt.device), idx]).unsqueeze(1)      # svd_flip(u=None, v-based)
+        scores = X @ Vt.t() - (mean.unsqueeze(0) @ Vt.t())        # PCA._transform
+    elif solver == "full":
+        U, S, Vt = torch.linalg.svd(X - mean, full_matrices=False)
+        idx = Vt.abs().argmax(dim=1)
+        signs = torch.sign(Vt[torch.arange(Vt.shape[0], device=Vt.device), idx])
+        scores = (U * signs.unsqueeze(0))[:, :n_comps] * S[:n_comps]
+    else:
+        raise NotImplementedError(f"PCA solver '{solver}'")
+    return scores.to(torch.float32).contiguous()
+
+
 def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_comps: Optional[int] = None,
                    simt: bool = False, info: Optional[dict] = None) -> torch.Tensor:
     """PCA scores (n_samples x n_comps, float32, device) of the residual matrix.
@@ -351,9 +380,12 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         n_comps = min_dim - 1 if N_PCS >= min_dim else N_PCS     # scanpy's n_comps rule
     solver = pca_solver(n_samples, n_features, n_comps)
     if solver != "randomized":
-        raise NotImplementedError(
-            f"sklearn PCA(svd_solver='auto') picks '{solver}' for shape ({n_samples}, {n_features}); only the "
-            "randomized solver (the one the GeneClust configurations hit) is implemented on the device")
+        if comm is not None:
+            raise NotImplementedError(f"PCA solver '{solver}' (small matrices) is not available on gene-sharded input")
+        scores = _small_pca(op, samples, solver, n_comps)
+        if info is not None:
+            info.update(solver=solver, n_comps=n_comps, passes=0)
+        return scores
     q = n_comps + N_OVERSAMPLES
     if q > Q_LD:
         raise NotImplementedError("n_components + 10 must be <= 64")

@@ -188,3 +188,25 @@ def test_device_omega_equals_numpy_randomstate(torch_cuda, seed, rows, q):
     ref = np.random.RandomState(seed).normal(size=(rows, q)).astype(np.float32)
     assert np.array_equal(got[:, :q], ref)
     assert not got[:, q:].any()
+
+
+@pytest.mark.parametrize("cells,genes,expect", [(300, 4000, "covariance_eigh"), (260, 320, "full")])
+def test_small_input_pca_solvers_vs_sklearn(torch_cuda, cells, genes, expect):
+    """Small inputs make sklearn's 'auto' policy leave the randomized solver (few-hundred-cell data sets: gene PCA runs
+    'covariance_eigh'; tiny matrices: 'full'); the device path follows it and matches the oracle's scores."""
+    from oracle import stages
+    from oracle.synth import synth_counts
+    from scgeneclust_b200._device import ResidualOperator, ingest_counts, pca_solver, randomized_pca
+    from scgeneclust_b200.synth import synth_params
+    p = synth_params(genes, 2)
+    X = synth_counts(p, 0, cells, 0, genes)
+    X = np.ascontiguousarray(X[:, (X > 0).sum(0) >= 3])
+    assert pca_solver(X.shape[1], X.shape[0], 50) == expect
+    op = ResidualOperator.from_counts(ingest_counts(X))
+    info = {}
+    got = randomized_pca(op, 'genes', 0, info=info).cpu().numpy()
+    assert info['solver'] == expect
+    ref = stages.gene_pca(stages.pearson_residuals(X.astype(np.float32)), 0)
+    rel = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
+    print(f"{expect}: {X.shape}, max per-component rel err {rel.max():.2e}")
+    assert got.shape == ref.shape and rel.max() <= 1e-3
