@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeneclust_b200.so")
+# GENECLUST_B200_LIB: developer override (kernel-variant timing, scripts/pass_times.py); the in-tree build is the default
+LIB_PATH = os.environ.get("GENECLUST_B200_LIB") or os.path.join(_HERE, "libgeneclust_b200.so")
 
 _p = C.c_void_p
 _i32, _i64, _u64, _f32, _f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double

@@ -211,6 +211,9 @@ template <bool LO_CLIP, bool ROW_R>
 __device__ __forceinline__ void resid8(const uint4 &raw, const float (&cr)[8], float fixed, float inv_theta, float clip,
                                        uint32_t magic, uint4 &hi, uint4 &lo) {
     // ROW_R: `fixed` is the row constant r and cr[] the per-column t;  else `fixed`... (same product either way)
+#ifdef TC_DBG_NOMATH      // ablation build (scripts/build_variant.py): keep the stores / MMAs, drop the residual math
+    hi = raw; lo = raw; return;
+#endif
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
     uint32_t h[4], l[4];
 #pragma unroll
@@ -380,6 +383,9 @@ rsvd_apply_tc_kernel(const TcArgs a) {
         uint4 raw[TC_CHUNKS];
         float cst[8];                  // TRANS 0: t of the stage's 8 genes of this thread; TRANS 1: r of its 8 cells
         auto load_chunk = [&](int it, int j) {
+#ifdef TC_DBG_NOLOAD      // ablation build: only the first group-stage is read from HBM
+            if (it >= TC_GROUPS) return;
+#endif
             const int64_t kk = k_lo + (int64_t)it * TC_TK;
             if constexpr (TRANS == 0) {
                 const int32_t row = min((int32_t)(m0 + a_row0 + A_ROW_STEP * j), c_last);
