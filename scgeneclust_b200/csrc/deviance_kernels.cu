@@ -59,33 +59,100 @@ __global__ void pairwise_combine_kernel(float *__restrict__ partial, int depth, 
     if (threadIdx.x == 0) out[blockIdx.x] = p[0];
 }
 
-// out[j] = a[0, j] + a[1, j] + ... sequentially (numpy add.reduce over the outer axis of a C-ordered (C, m) array, m > 1)
-// one CTA per 32 columns; rows are staged through shared memory 64 at a time so the loads are coalesced and off the chain
-__global__ void __launch_bounds__(256)
-colsum_sequential_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m,
+// out[j] = a[0, j] + a[1, j] + ... sequentially (numpy add.reduce over the outer axis of a C-ordered (C, m) array, m > 1).
+// The C-long dependent float32 add chain per column is the cost (4 cycles per row is the floor); everything else is
+// kept off it: one CTA per block of columns (all of them when m <= 256, else 64: longer stages, more CTAs), whole row
+// blocks stream into a 3-stage shared-memory ring with
+// cp.async two stages ahead (16-byte copies when the block is the full row width, i.e. m <= 256, and the array is
+// 16-byte aligned), thread j adds column j of the stage row after row.
+constexpr int kColStages = 3, kColStageFloats = 4096, kColThreads = 256;
+
+__device__ __forceinline__ void cp_async4(float *dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float *dst, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kColThreads)
+colsum_sequential_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m, int cb,
                          float *__restrict__ out0, float *__restrict__ out1) {
     // blockIdx.y selects the array: the left and right halves of the deviance are summed by concurrent CTAs
     const float *__restrict__ a = blockIdx.y == 0 ? a0 : a1;
     float *__restrict__ out = blockIdx.y == 0 ? out0 : out1;
-    __shared__ float tile[64][33];
-    const int j0 = blockIdx.x * 32;
-    const int tj = threadIdx.x & 31, ti = threadIdx.x >> 5;          // 8 row lanes x 32 columns
+    __shared__ __align__(16) float ring[kColStages][kColStageFloats];
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * cb, mc = min(cb, m - j0);            // cb <= kColThreads columns per CTA
+    const bool flat = mc == m;                                       // the block is whole rows: one contiguous range per stage
+    const bool vec = flat && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+    int R = max(1, kColStageFloats / mc);                            // rows per stage
+    if (R >= 8) R -= R % 8;                                          // stage starts stay 16-byte aligned (R m floats)
+    else if (R >= 4) R = 4;
+    const int64_t n_stage = ceil_div<int64_t>(C, R);
+
+    auto issue = [&](int64_t s) {
+        if (s < n_stage) {
+            const int64_t i0 = s * R;
+            const int n = (int)min((int64_t)R, C - i0) * mc;
+            float *dst = ring[s % kColStages];
+            if (flat) {
+                const float *src = a + i0 * m;
+                int done = 0;
+                if (vec) {
+                    done = n & ~3;
+                    for (int e = 4 * tid; e < done; e += 4 * kColThreads) cp_async16(dst + e, src + e);
+                }
+                for (int e = done + tid; e < n; e += kColThreads) cp_async4(dst + e, src + e);
+            } else {
+                for (int e = tid; e < n; e += kColThreads) {
+                    const int r = e / mc, c = e - r * mc;
+                    cp_async4(dst + e, a + (i0 + r) * m + j0 + c);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per stage, empty past the end
+    };
+
+    for (int s = 0; s < kColStages - 1; ++s) issue(s);
     float acc = 0.f;
-    for (int64_t i0 = 0; i0 < C; i0 += 64) {
-        __syncthreads();
+    for (int64_t s = 0; s < n_stage; ++s) {
+        issue(s + kColStages - 1);                                    // into the slot the previous iteration consumed
+        asm volatile("cp.async.wait_group %0;" ::"n"(kColStages - 1) : "memory");
+        __syncthreads();                                              // stage s of every thread has landed
+        if (tid < mc) {
+            const float *p = ring[s % kColStages] + tid;
+            const int rows = (int)min((int64_t)R, C - s * R);
+            int r = 0;
+            if (s == 0) { acc = p[0]; r = 1; }                        // the reduction starts from the first row
+            // blocks of 8 rows in two register sets: the shared-memory loads of the next block are issued (unconditionally,
+            // row index clamped) before the adds of the current one, so only the adds are on the dependent chain
+            const int nb = (rows - r) >> 3, last = rows - 1;
+            float c[8], nx[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int64_t i = i0 + ti + 8 * r;
-            tile[ti + 8 * r][tj] = (i < C && j0 + tj < m) ? a[i * m + j0 + tj] : 0.f;
+            for (int k = 0; k < 8; ++k) c[k] = p[min(r + k, last) * mc];
+            int b = 0;
+#pragma unroll 1
+            for (; b + 1 < nb; b += 2) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) nx[k] = p[min(r + 8 + k, last) * mc];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = acc + c[k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c[k] = p[min(r + 16 + k, last) * mc];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = acc + nx[k];
+                r += 16;
+            }
+            if (b < nb) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc = acc + c[k];
+                r += 8;
+            }
+            for (; r < rows; ++r) acc = acc + p[r * mc];
         }
-        __syncthreads();
-        if (ti == 0) {
-            const int rows = (int)min((int64_t)64, C - i0);
-            if (i0 == 0) { acc = tile[0][tj]; for (int r = 1; r < rows; ++r) acc = acc + tile[r][tj]; }
-            else for (int r = 0; r < rows; ++r) acc = acc + tile[r][tj];
-        }
+        __syncthreads();                                              // slot free for the stage issued next iteration
     }
-    if (ti == 0 && j0 + tj < m) out[j0 + tj] = acc;
+    if (tid < mc) out[j0 + tid] = acc;
 }
 
 // per row: n_i = pairwise sum of the row; L[i,j], R[i,j] with NaN -> 0 (np.nansum's _replace_nan)
@@ -137,6 +204,7 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
     float *left = (float *)p;      p += dev_align((int64_t)m * 4 + 16);
     float *right = (float *)p;
     const int64_t n_all = C * (int64_t)m;
+    const int cb = m <= kColThreads ? kColThreads : 64;      // columns per CTA of the sequential column sums
     const int depth = pairwise_depth(n_all);
     const int n_sub = 1 << depth;
     // X.sum() (and, for m == 1, the column sum is the same number)
@@ -147,7 +215,7 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
     if (m == 1) {
         GC_CUDA(cudaMemcpyAsync(colsum, total, sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, 32), 1), 256, 0, st>>>(X, nullptr, C, m, colsum, nullptr);
+        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, cb), 1), kColThreads, 0, st>>>(X, nullptr, C, m, cb, colsum, nullptr);
         if (int rc = check_launch("colsum_sequential_kernel")) return rc;
     }
     deviance_terms_kernel<<<(unsigned)ceil_div<int64_t>(C, 128), 128, 0, st>>>(X, C, m, colsum, total, L, R);
@@ -160,7 +228,7 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
         // the second block wrote left[1]; move it to right[0]
         GC_CUDA(cudaMemcpyAsync(right, left + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, 32), 2), 256, 0, st>>>(L, R, C, m, left, right);
+        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, cb), 2), kColThreads, 0, st>>>(L, R, C, m, cb, left, right);
         if (int rc = check_launch("colsum_sequential_kernel")) return rc;
     }
     deviance_finish_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(left, right, m, out);

@@ -564,17 +564,19 @@ __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_
     reinterpret_cast<float4 *>(Y)[i] = s;
 }
 
-// split-K heuristic: fill a whole number of waves of 148 CTAs (one per SM)
+// split-K heuristic (one CTA per SM): minimise  waves x (stages per CTA + fixed cost of a CTA), the fixed cost (barrier /
+// TMEM set-up, first loads, epilogue: ~3 us) counted as 4 stages; among choices within 1.5 % the fewest slabs win
+// (less partial traffic).  50 000 x 20 000: 3 slabs for M Q (8 waves), 13 for M^T Q; with the genes sharded 8 ways
+// (400 000 x 2 500 per GPU) M Q runs unsplit instead of doubling the CTA count for 2 % better wave filling.
 __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
     const int64_t slots = (int64_t)kNumSMs;
     int best = 1;
-    double best_eff = 0.0;
+    int64_t best_cost = 0;
     for (int s = 1; s <= 64; ++s) {
         const int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(n_k, s), TC_TK) * TC_TK;
-        if (s > 1 && k_per < 16 * TC_TK) break;
-        const int64_t ctas = n_tiles * s;
-        const double eff = (double)ctas / (double)(ceil_div<int64_t>(ctas, slots) * slots);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+        if (s > 1 && k_per < 8 * TC_TK) break;
+        const int64_t cost = ceil_div<int64_t>(n_tiles * s, slots) * (k_per / TC_TK + 4);
+        if (s == 1 || cost * 1000 < best_cost * 985) { best_cost = cost; best = s; }
     }
     return best;
 }

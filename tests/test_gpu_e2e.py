@@ -150,7 +150,7 @@ def test_ps_entry_point_end_to_end(torch_cuda, data):
     assert (s >= 0).all() and (s <= 1).all()
 
 
-@pytest.mark.parametrize("C,m", [(3001, 1), (3001, 2), (50000, 1), (50000, 7), (20011, 40)])
+@pytest.mark.parametrize("C,m", [(3001, 1), (3001, 2), (50000, 1), (50000, 7), (20011, 40), (4099, 300), (131075, 5)])
 def test_device_deviance_equals_numpy(torch_cuda, C, m):
     """Singleton rescue: the device binomial deviance must be the reference's numpy expression
     (scGeneClust/tl/selection.py:82-89) on float32 residual-like columns, including its NaN handling; equality up to
@@ -164,8 +164,13 @@ def test_device_deviance_equals_numpy(torch_cuda, C, m):
     ref = compute_deviance(X)
     got = device_deviance(torch.from_numpy(X).cuda())
     assert got.dtype == np.float32 and got.shape == (m,)
+    # a 4-byte-aligned view of the same block takes the narrow-copy path of the column-sum kernel: same bits
+    flat = torch.zeros(C * m + 1, dtype=torch.float32, device="cuda")
+    flat[1:].view(C, m).copy_(torch.from_numpy(X))
+    assert np.array_equal(device_deviance(flat[1:].view(C, m)).view(np.uint32), got.view(np.uint32))
     # left and right halves (~1e4) cancel to ~1e2..1e3, which amplifies the last-bit logf differences to ~1e-6 relative
-    assert np.allclose(got, ref, rtol=2e-5, atol=0, equal_nan=True), (got, ref)
+    # (with 300 columns the worst column cancels harder: 1e-4)
+    assert np.allclose(got, ref, rtol=2e-5 if m <= 64 else 1e-4, atol=0, equal_nan=True), (got, ref)
     print(f"deviance C={C} m={m}: identical {int((got == ref).sum())}/{m}, max rel {np.max(np.abs(got - ref) / np.abs(ref)):.1e}")
 
 
