@@ -299,6 +299,21 @@ __device__ __forceinline__ float sqdist_prepared(const float *__restrict__ xc, d
 // for round 1): adopt the winner's distances, sequential float32 cumsum staged through shared memory, searchsorted of
 // the next uniforms inside shared memory.
 constexpr int kRoundChunk = 6144;     // floats of cumsum staged per pass of the tail (24 KB)
+constexpr int kSpecP = 64;            // pieces of the speculative running sum (see the tail of kpp_round_kernel)
+
+// exact sequential float32 sum of q[0..len) started from acc; loads batched ahead of the dependent adds
+__device__ __forceinline__ float chain_sum(const float *q, int len, float acc) {
+    int i = 0;
+    for (; i + 8 <= len; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = q[i + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = acc + v[k];
+    }
+    for (; i < len; ++i) acc = acc + q[i];
+    return acc;
+}
 __global__ void __launch_bounds__(kKppThreads)
 kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
                  const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
@@ -307,7 +322,9 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
     __shared__ float sc[kDMax];
     __shared__ double sxx;
     __shared__ double red[kKppThreads];
-    __shared__ __align__(16) float buf[kRoundChunk + 32];    // + zero padding: the scan reads one block ahead
+    __shared__ __align__(16) float buf[kRoundChunk + 2 * kSpecP + 32];    // + zero padding up to kSpecP pieces of odd length
+    __shared__ float sp_sum[kSpecP], sp_d0[kSpecP], sp_d1[kSpecP], sp_start[kSpecP], sp_end[kSpecP];
+    __shared__ int sp_e[kSpecP];
     __shared__ float carry;
     __shared__ int s_best, s_is_last;
     __shared__ float s_pot;
@@ -413,39 +430,96 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
                     closest[c0 + i] = v;
                 }
             }
-            for (int i = cn + threadIdx.x; i < ((cn + 15) & ~15) + 16; i += blockDim.x) buf[i] = 0.f;   // x + 0 = x
+            for (int i = cn + threadIdx.x; i < cn + 2 * kSpecP + 32; i += blockDim.x) buf[i] = 0.f;   // x + 0 = x
+        }
+        __syncthreads();
+        // np.cumsum(closest) is a dependent float32 add chain (4 cycles per element, 6 000 elements) and only its
+        // crossings of the n_trials targets are needed.  Speculative exact evaluation (scripts/proto/spec_cumsum.py is
+        // the CPU prototype, checked bit for bit against np.cumsum): the chunk is cut into kSpecP pieces of odd length
+        // (bank-conflict free).  While the running sum stays inside one binade [2^e, 2^(e+1)), every add rounds to a
+        // multiple of u = ulp and only round-half-to-even looks at the sum itself - at its last mantissa bit.  So the
+        // amount a piece adds depends on the start value only through (e, parity): each thread runs its piece from the
+        // two SURROGATE starts 2^e and 2^e + u (e guessed from approximate prefix sums) and records the increments
+        // D[parity]; one thread then walks the pieces, end = start + D[parity(start)], accepting a piece iff the
+        // start really has exponent e and the end still has it (monotone sums: no add left the binade; the
+        // surrogates are <= the true start, so they did not leave it either), and summing the piece for real
+        // otherwise (~6 of 64 pieces: the ones in which the sum crosses a power of two).  Finally each target is
+        // located inside its piece by a real chain from the exact piece start.
+        const int len = ((cn + kSpecP - 1) / kSpecP) | 1;
+        if (threadIdx.x < kSpecP) {
+            const float *q = buf + threadIdx.x * len;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int i = 0;
+            for (; i + 4 <= len; i += 4) { s0 += q[i]; s1 += q[i + 1]; s2 += q[i + 2]; s3 += q[i + 3]; }
+            for (; i < len; ++i) s0 += q[i];
+            sp_sum[threadIdx.x] = (s0 + s1) + (s2 + s3);
+        }
+        __syncthreads();
+        if (threadIdx.x < kSpecP) {
+            const int p = threadIdx.x;
+            const float *q = buf + p * len;
+            if (p == 0) {
+                sp_start[0] = carry;
+                sp_end[0] = chain_sum(q, len, carry);
+            } else {
+                float a0 = carry, a1 = 0.f, a2 = 0.f, a3 = 0.f;         // approximate start (any order)
+                int j = 0;
+                for (; j + 4 <= p; j += 4) { a0 += sp_sum[j]; a1 += sp_sum[j + 1]; a2 += sp_sum[j + 2]; a3 += sp_sum[j + 3]; }
+                for (; j < p; ++j) a0 += sp_sum[j];
+                const int e = (int)((__float_as_uint((a0 + a1) + (a2 + a3)) >> 23) & 0xffu);
+                const float lo0 = __uint_as_float((uint32_t)e << 23), lo1 = __uint_as_float(((uint32_t)e << 23) + 1u);
+                float x0 = lo0, x1 = lo1;
+                int i = 0;
+                for (; i + 4 <= len; i += 4) {
+                    const float v0 = q[i], v1 = q[i + 1], v2 = q[i + 2], v3 = q[i + 3];
+                    x0 = x0 + v0; x1 = x1 + v0; x0 = x0 + v1; x1 = x1 + v1;
+                    x0 = x0 + v2; x1 = x1 + v2; x0 = x0 + v3; x1 = x1 + v3;
+                }
+                for (; i < len; ++i) { const float v = q[i]; x0 = x0 + v; x1 = x1 + v; }
+                sp_d0[p] = x0 - lo0;
+                sp_d1[p] = x1 - lo1;
+                sp_e[p] = (e >= 1 && e <= 253) ? e : -1;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            // the dependent float32 add chain of np.cumsum (4 cycles per element).  Blocks of 16; the shared-memory
-            // loads of the next block are issued before the chain of the current one (the zero padding makes the
-            // read-ahead of the last block harmless), so only the adds are on the critical path.
-            float acc = carry;
-            float4 *b4 = reinterpret_cast<float4 *>(buf);
-            const int nb = (cn + 15) >> 4;
-            float4 a0 = b4[0], a1 = b4[1], a2 = b4[2], a3 = b4[3];
-#pragma unroll 1
-            for (int b = 0; b < nb; ++b) {
-                const float4 n0 = b4[4 * b + 4], n1 = b4[4 * b + 5], n2 = b4[4 * b + 6], n3 = b4[4 * b + 7];
-                acc = acc + a0.x; a0.x = acc; acc = acc + a0.y; a0.y = acc; acc = acc + a0.z; a0.z = acc; acc = acc + a0.w; a0.w = acc;
-                acc = acc + a1.x; a1.x = acc; acc = acc + a1.y; a1.y = acc; acc = acc + a1.z; a1.z = acc; acc = acc + a1.w; a1.w = acc;
-                acc = acc + a2.x; a2.x = acc; acc = acc + a2.y; a2.y = acc; acc = acc + a2.z; a2.z = acc; acc = acc + a2.w; a2.w = acc;
-                acc = acc + a3.x; a3.x = acc; acc = acc + a3.y; a3.y = acc; acc = acc + a3.z; a3.z = acc; acc = acc + a3.w; a3.w = acc;
-                b4[4 * b] = a0; b4[4 * b + 1] = a1; b4[4 * b + 2] = a2; b4[4 * b + 3] = a3;
-                a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+            float start = sp_end[0];
+#pragma unroll 4
+            for (int p = 1; p < kSpecP; ++p) {
+                sp_start[p] = start;
+                const uint32_t sb = __float_as_uint(start);
+                const int es = (int)((sb >> 23) & 0xffu);
+                float end = start + ((sb & 1u) ? sp_d1[p] : sp_d0[p]);
+                const bool ok = es == sp_e[p] && (int)((__float_as_uint(end) >> 23) & 0xffu) == es;
+                if (!ok) end = chain_sum(buf + p * len, len, start);
+                sp_end[p] = end;
+                start = end;
             }
-            carry = acc;
+            carry = start;
         }
         __syncthreads();
-        if (threadIdx.x < n_trials && s_found[threadIdx.x] < 0 && (double)buf[cn - 1] >= s_rv[threadIdx.x]) {
-            // np.searchsorted(cumsum, rv, side='left') restricted to this chunk (earlier chunks are all < rv)
-            const double rv = s_rv[threadIdx.x];
-            int lo = 0, hi = cn;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if ((double)buf[mid] < rv) lo = mid + 1; else hi = mid;
+        if (threadIdx.x < n_trials && s_found[threadIdx.x] < 0) {
+            // np.searchsorted(cumsum, rv, side='left') restricted to this chunk (earlier chunks are all < rv).  For a
+            // float32 c:  (double)c >= rv  <=>  c >= rv rounded UP to float32
+            const float rvf = __double2float_ru(s_rv[threadIdx.x]);
+            if (sp_end[kSpecP - 1] >= rvf) {
+                int lo = 0, hi = kSpecP - 1;                           // first piece whose end reaches the target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sp_end[mid] < rvf) lo = mid + 1; else hi = mid;
+                }
+                const float *q = buf + lo * len;
+                float acc = sp_start[lo];
+                int i = 0;
+                for (; i + 8 <= len; i += 8) {                         // blocks of 8: one test per block on the chain
+                    const float before = acc;
+                    const float nxt = chain_sum(q + i, 8, acc);
+                    if (nxt >= rvf) { acc = before; break; }
+                    acc = nxt;
+                }
+                for (; i < len; ++i) { acc = acc + q[i]; if (acc >= rvf) break; }
+                s_found[threadIdx.x] = c0 + lo * len + i;
             }
-            s_found[threadIdx.x] = c0 + lo;
         }
     }
     __syncthreads();
