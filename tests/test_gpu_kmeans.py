@@ -56,19 +56,30 @@ def test_assign_and_update_kernels_vs_numpy(torch_cuda):
     assert np.array_equal(dW.cpu().numpy(), w_ref)
 
 
-def test_kmeanspp_matches_sklearn(torch_cuda):
-    """Device k-means++ draws the same centre indices as sklearn's `_kmeans_plusplus` from the same RandomState."""
+@pytest.mark.parametrize("kind,n", [("normal", 3000), ("normal", 7000), ("grid", 6000), ("grid", 7000), ("dups", 6000)])
+def test_kmeanspp_matches_sklearn(torch_cuda, kind, n):
+    """Device k-means++ draws the same centre indices as sklearn's `_kmeans_plusplus` from the same RandomState.
+    The candidate draw is `searchsorted(cumsum(closest_dist_sq), u * pot)` on a sequential float32 cumsum, which the
+    round kernel evaluates speculatively (kmeans_kernels.cu): 'grid' (half-integer coordinates: squared distances with
+    few mantissa bits whose running sum passes 2^24, so round-half-to-even ties are frequent) and 'dups' (duplicated
+    rows: exact zeros, equal values) stress its parity / binade logic; n = 7000 spans two staged chunks."""
     torch = torch_cuda
     from sklearn.cluster._kmeans import _kmeans_plusplus
     from sklearn.utils.extmath import row_norms
     from scgeneclust_b200.tl.cluster import DeviceMiniBatchKMeans
     rs = np.random.RandomState(4)
-    X = (rs.standard_normal((3000, 50)) * (3.0 / np.sqrt(1 + np.arange(50)))).astype(np.float32)
+    if kind == "normal":
+        X = (rs.standard_normal((n, 50)) * (3.0 / np.sqrt(1 + np.arange(50)))).astype(np.float32)
+    elif kind == "grid":
+        X = (rs.randint(-64, 65, (n, 50)) * 0.5).astype(np.float32)
+    else:
+        base = (rs.standard_normal((n // 4, 50)) * 2.0).astype(np.float32)
+        X = base[rs.randint(0, len(base), n)]
     K = 60
-    _, idx_ref = _kmeans_plusplus(X, K, row_norms(X, squared=True), np.ones(3000, np.float32),
+    _, idx_ref = _kmeans_plusplus(X, K, row_norms(X, squared=True), np.ones(n, np.float32),
                                   np.random.RandomState(7))
     km = DeviceMiniBatchKMeans(K, 1024, 7)
-    centers = km._init_centroids(torch.from_numpy(X).cuda(), np.random.RandomState(7), 3000)
+    centers = km._init_centroids(torch.from_numpy(X).cuda(), np.random.RandomState(7), n)
     idx = km.init_indices_.cpu().numpy()
     assert np.array_equal(idx, idx_ref)
     assert np.array_equal(centers.cpu().numpy(), X[idx_ref])

@@ -266,3 +266,26 @@ def test_glosh_scores_and_noise_labels_on_separated_blobs():
     rec = np.zeros(len(pts) - 1, dtype=_linkage.MST_edge_dtype)
     rec['current_node'], rec['next_node'], rec['distance'] = edges[:, 0].astype(np.intp), edges[:, 1].astype(np.intp), edges[:, 2]
     assert np.array_equal(labels, _tree.tree_to_labels(_linkage.make_single_linkage(rec), 3, "eom", False, 0.0, None)[0])
+
+
+def test_speculative_cumsum_prototype_is_bit_exact():
+    """The algorithm of the k-means++ round kernel's running sum (scripts/proto/spec_cumsum.py): piece-parallel
+    evaluation of a sequential float32 cumsum from surrogate starts, verified piece by piece - must reproduce the
+    dependent chain bit for bit, including ties (few mantissa bits), zeros, outliers and 20 binades of range."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "proto", "spec_cumsum.py")
+    spec = importlib.util.spec_from_file_location("spec_cumsum", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rs = np.random.RandomState(11)
+    reals = []
+    for trial in range(24):
+        cn = int(rs.choice([6000, 6144, 777, 65, 3]))
+        v = [rs.gamma(2.0, 30.0, cn),
+             rs.gamma(2.0, 30.0, cn) * (rs.rand(cn) < 0.5),
+             np.ldexp(rs.randint(1, 64, cn).astype(np.float64), rs.randint(-6, 3, cn)),
+             rs.lognormal(0, 4, cn)][trial % 4].astype(np.float32)
+        carry = 0.0 if trial % 3 else float(np.float32(rs.gamma(2.0, 1e5)))
+        reals.append(mod.check(v, carry))          # asserts bit equality at every piece boundary
+    assert np.mean(reals) < 20                     # and most pieces are resolved without a real chain
