@@ -80,12 +80,13 @@ class AnnDataLite:
         self._X = X
         n_obs, n_vars = X.shape
         if obs is None:
-            # default names ('cell_0', ... / 'gene_0', ...) are materialised on first use of `obs_names` / `var_names`
+            # names are kept as an object-dtype Index (pandas 3 would otherwise spend 1-2 ms per 20 000 names inferring
+            # its arrow string dtype); default names ('cell_0', ... / 'gene_0', ...) are materialised on first use of `obs_names` / `var_names`
             # (building 10^5..10^6 strings up front would cost more than the whole device pipeline)
-            index = pd.Index(np.asarray(obs_names, dtype=object)) if obs_names is not None else pd.RangeIndex(n_obs)
+            index = pd.Index(np.asarray(obs_names, dtype=object), dtype=object) if obs_names is not None else pd.RangeIndex(n_obs)
             obs = pd.DataFrame(index=index)
         if var is None:
-            index = pd.Index(np.asarray(var_names, dtype=object)) if var_names is not None else pd.RangeIndex(n_vars)
+            index = pd.Index(np.asarray(var_names, dtype=object), dtype=object) if var_names is not None else pd.RangeIndex(n_vars)
             var = pd.DataFrame(index=index)
         if len(obs) != n_obs or len(var) != n_vars:
             raise ValueError("obs/var length does not match X")
@@ -119,7 +120,7 @@ class AnnDataLite:
     @staticmethod
     def _named(frame: pd.DataFrame, prefix: str) -> pd.Index:
         if isinstance(frame.index, pd.RangeIndex):
-            frame.index = pd.Index(np.char.add(prefix, np.arange(len(frame)).astype(str)).astype(object))
+            frame.index = pd.Index(np.char.add(prefix, np.arange(len(frame)).astype(str)).astype(object), dtype=object)
         return frame.index
 
     @property
