@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from oracle.synth import cell_types
+from scgeneclust_b200.synth import synth_cell_types as cell_types
 from scgeneclust_b200 import AnnDataLite, pp, tl
 from scgeneclust_b200.synth import DeviceSynth, synth_params
 from scgeneclust_b200.tl.cluster import generate_gene_clusters
