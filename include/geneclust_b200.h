@@ -49,10 +49,14 @@ int gc_fp64_probe(double *ops_per_s_host, double *scratch_dev, void *stream);
  * scGeneClust/_validation.py:68-70.
  * ------------------------------------------------------------------------------------------------------- */
 /* CSR (float32 data, int32 indices, int64 indptr, `n_rows` rows starting at global row `row0` of the dense
- * matrix) -> dense uint16 counts[C x ld].  flags[0] is set to 1 if a value is not a non-negative integer,
- * flags[1] to 1 if a value exceeds 65535.  The destination rows must be zeroed by the caller. */
+ * matrix, G columns) -> dense uint16 counts[C x ld].  flags (4 x int32, zeroed by the caller) are set to 1 when:
+ * [0] a value is not a non-negative integer, [1] a value or a sum of duplicates exceeds 65535, [2] a column index is
+ * outside [0, G), [3] (accumulate == 0 only) a row is not canonical, i.e. its indices are not strictly increasing.
+ * accumulate == 0: plain stores, correct for canonical rows; accumulate != 0: duplicate entries are summed, as scipy's
+ * toarray() does for the reference (scGeneClust/_model.py:124).  The destination rows must be zeroed by the caller. */
 int gc_csr_to_counts(const float *data, const int32_t *indices, const int64_t *indptr, int64_t n_rows,
-                     int64_t row0, uint16_t *counts, int64_t ld, int32_t *flags, void *stream);
+                     int64_t row0, int64_t G, uint16_t *counts, int64_t ld, int accumulate, int32_t *flags,
+                     void *stream);
 /* Dense float32 block (n_rows x G, leading dimension ld_src) -> uint16 counts rows [row0, row0+n_rows). */
 int gc_dense_to_counts(const float *src, int64_t ld_src, int64_t n_rows, int64_t G, int64_t row0,
                        uint16_t *counts, int64_t ld, int32_t *flags, void *stream);

@@ -40,6 +40,19 @@ def pearson_residuals(X: np.ndarray, theta: float = THETA) -> np.ndarray:
     return np.clip(residuals, -clip, clip).astype(dt, copy=False)
 
 
+def pearson_residuals_block(X_block: np.ndarray, sums_cells: np.ndarray, sums_genes: np.ndarray, sum_total: float,
+                            n_cells_total: int, theta: float = THETA) -> np.ndarray:
+    """The same formula for a sub-block of a larger matrix whose sums are given (`sums_cells`: the block's cells,
+    `sums_genes`: the block's genes, both over the FULL matrix; clip = sqrt(number of cells of the full matrix)).
+    Lets the full-size tests check sampled blocks of a matrix that never exists on the host."""
+    X = np.asarray(X_block, dtype=np.float32)
+    clip = np.float32(np.sqrt(n_cells_total))
+    mu = np.asarray(sums_cells, dtype=np.float32).reshape(-1, 1) @ np.asarray(sums_genes, dtype=np.float32).reshape(1, -1)
+    mu = mu / np.float32(sum_total)
+    residuals = (X - mu) / np.sqrt(mu + mu ** 2 / np.float32(theta))
+    return np.clip(residuals, -clip, clip).astype(np.float32, copy=False)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # a2  pp.reduce_dim                                  scGeneClust/pp/_preprocessing.py:35-55
 # ---------------------------------------------------------------------------------------------------------

@@ -12,6 +12,10 @@ of the cdf.  Per-cell factors are quantised to 64 levels selected by hashing so 
 """
 from __future__ import annotations
 
+import ctypes
+import os
+from types import SimpleNamespace
+
 import numpy as np
 
 U64 = np.uint64
@@ -69,3 +73,61 @@ def synth_counts(p, c0: int, nc: int, g0: int, ng: int) -> np.ndarray:
         still = (u[idx] > cd) & (kk < 65535) & (pm > 0.0)
         active[idx] = still
     return k.astype(np.uint16)
+
+
+def synth_params(G: int, seed: int = 0, n_types: int = 8, n_modules: int = 40, module_size: int = 50):
+    """The generator's parameter tables - the oracle's own copy of `scgeneclust_b200.synth.synth_params` (same draws
+    from RandomState(seed) in the same order; equality is checked in tests/test_host_logic.py), so the CPU reference
+    arm of bench.py builds its input without importing anything of the product package."""
+    rs = np.random.RandomState(seed)
+    gene_mean = np.clip(np.exp(rs.normal(-1.5, 1.5, G)), 0.01, 50.0)
+    type_fc = np.ones((G, n_types))
+    n_mark = max(1, int(0.05 * G))
+    for t in range(n_types):
+        markers = rs.choice(G, n_mark, replace=False)
+        type_fc[markers, t] = 2.0 ** rs.normal(0.0, 1.5, n_mark)
+    gene_module = np.full(G, -1, np.int32)
+    n_in = min(G, n_modules * module_size)
+    members = rs.permutation(G)[:n_in]
+    gene_module[members] = (np.arange(n_in) // module_size).astype(np.int32)
+    size_levels = np.exp(rs.normal(0.0, 0.3, 64))
+    module_levels = np.exp(rs.normal(0.0, 0.5, 64))
+    return SimpleNamespace(seed=seed, G=G, n_types=n_types, gene_mean=gene_mean,
+                           type_fc=np.ascontiguousarray(type_fc), gene_module=gene_module, size_levels=size_levels,
+                           module_levels=module_levels, n_modules=n_modules)
+
+
+_CLIB = None
+
+
+def _clib():
+    """oracle/_build/liboracle_synth.so (oracle/synth_c.c), built on first use when gcc is present."""
+    global _CLIB
+    if _CLIB is None:
+        from .build_c import LIB, build
+        path = LIB if os.path.exists(LIB) else build()
+        dll = ctypes.CDLL(path)
+        p = ctypes.c_void_p
+        dll.oracle_synth_counts.restype = None
+        dll.oracle_synth_counts.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int64, p, p, ctypes.c_int, p, p, ctypes.c_int, p, ctypes.c_int,
+                                            p, ctypes.c_int64]
+        _CLIB = dll
+    return _CLIB
+
+
+def synth_counts_c(p, c0: int, nc: int, g0: int = 0, ng: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """Same block as `synth_counts`, from the C twin (oracle/synth_c.c, OpenMP over cells): what the full-size CPU
+    arms use (the numpy version takes ~0.1 s per cell).  `out`: optional preallocated uint16 [nc, >= ng] C-order."""
+    ng = p.G - g0 if ng is None else ng
+    if out is None:
+        out = np.empty((nc, ng), dtype=np.uint16)
+    assert out.dtype == np.uint16 and out.flags.c_contiguous and out.shape[0] == nc and out.shape[1] >= ng
+    gm = np.ascontiguousarray(p.gene_mean, dtype=np.float64)
+    fc = np.ascontiguousarray(p.type_fc, dtype=np.float64)
+    mod = np.ascontiguousarray(p.gene_module, dtype=np.int32)
+    sl = np.ascontiguousarray(p.size_levels, dtype=np.float64)
+    ml = np.ascontiguousarray(p.module_levels, dtype=np.float64)
+    _clib().oracle_synth_counts(p.seed, c0, nc, g0, ng, gm.ctypes.data, fc.ctypes.data, p.n_types, mod.ctypes.data,
+                                sl.ctypes.data, len(sl), ml.ctypes.data, len(ml), out.ctypes.data, out.shape[1])
+    return out[:, :ng]

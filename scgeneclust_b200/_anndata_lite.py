@@ -52,20 +52,32 @@ class DeviceMatrix:
         return DeviceMatrix(self.tensor.clone())
 
     def __getitem__(self, key):
+        """numpy indexing semantics.  `x[rows, :]` / `x[:, cols]` (one axis subset, the other a full slice) stay on the
+        device and return a DeviceMatrix; two index arrays are PAIRED like numpy's (`x[i, j]` -> the elements
+        x[i[k], j[k]], gathered on the device and returned as an ndarray); everything else goes through the host copy."""
         import torch
         if not (isinstance(key, tuple) and len(key) == 2):
             return np.asarray(self)[key]
-        t = self.tensor
-        for axis, k in enumerate(key):
-            if isinstance(k, slice) and k == slice(None):
+        full = [isinstance(k, slice) and k == slice(None) for k in key]
+        idx = []
+        for k, is_full in zip(key, full):
+            if is_full:
+                idx.append(None)
                 continue
             k = np.asarray(k)
-            if k.dtype == bool:
+            if k.dtype == bool and k.ndim == 1:
                 k = np.flatnonzero(k)
             if k.ndim != 1 or k.dtype.kind not in "iu":
                 return np.asarray(self)[key]
-            t = t.index_select(axis, torch.from_numpy(k.astype(np.int64)).to(t.device))
-        return DeviceMatrix(t.contiguous())
+            idx.append(torch.from_numpy(k.astype(np.int64)).to(self.tensor.device))
+        if all(full):
+            return self
+        if idx[0] is not None and idx[1] is not None:
+            if idx[0].numel() != idx[1].numel():
+                return np.asarray(self)[key]                     # let numpy broadcast or raise as it would
+            return self.tensor[idx[0], idx[1]].cpu().numpy()
+        axis = 0 if idx[0] is not None else 1
+        return DeviceMatrix(self.tensor.index_select(axis, idx[axis]).contiguous())
 
 
 class AnnDataLite:

@@ -74,27 +74,37 @@ class HostShard:
         return (self.array.shape[0], self.comm.total_genes)
 
 
-def _check_flags(flags: torch.Tensor):
+def _check_flags(flags: torch.Tensor, comm=None):
+    """Raise the ingest errors.  With a gene-shard communicator the flags are max-reduced first, so that every rank
+    raises together (a rank-local raise would leave the other ranks waiting in the next collective)."""
+    if comm is not None and comm.world > 1:
+        comm.all_reduce_max(flags)
     f = flags.cpu().numpy()
     if f[0]:
         # same message as the reference, scGeneClust/_validation.py:70
         raise ValueError("Expected raw counts, got normalized counts possibly.")
     if f[1]:
         raise ValueError("Counts above 65535 are not supported by the uint16 device layout.")
+    if f[2]:
+        raise ValueError("Sparse count matrix has column indices outside [0, n_vars).")
+    if f[4]:
+        raise ValueError("Expected raw counts, got negative values (int16 input).")
 
 
-def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
+def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192, comm=None) -> DeviceCounts:
     """Host (or device) count matrix -> `DeviceCounts`.  Never densifies on the host (contrast
-    scGeneClust/_model.py:124, _validation.py:68): CSR is expanded and validated on the device."""
+    scGeneClust/_model.py:124, _validation.py:68): CSR is expanded and validated on the device; a CSR matrix that is
+    not in canonical form (unsorted or duplicate column indices) has its duplicates summed, as `toarray()` does.
+    Host arrays are uploaded asynchronously when they sit in pinned memory."""
     require_cuda()
     L = lib()
     dev = torch.device(device)
     if isinstance(X, DeviceCounts):
         return X
     if isinstance(X, HostShard):
-        local = ingest_counts(X.array, device, rows_per_chunk)
-        if local.G != X.comm.local_genes:
-            raise ValueError(f"host shard has {local.G} genes, the communicator assigns {X.comm.local_genes}")
+        if X.array.shape[1] != X.comm.local_genes:
+            raise ValueError(f"host shard has {X.array.shape[1]} genes, the communicator assigns {X.comm.local_genes}")
+        local = ingest_counts(X.array, device, rows_per_chunk, comm=X.comm)
         local.comm = X.comm
         return local
     if isinstance(X, torch.Tensor):
@@ -110,7 +120,7 @@ def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
     C_, G_ = X.shape
     ld = _round_up(G_, 64)
     counts = torch.zeros((C_, ld), dtype=torch.int16, device=dev)
-    flags = torch.zeros(2, dtype=torch.int32, device=dev)
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
     st = stream_handle()
     if issparse(X):
         X = X.tocsr()
@@ -118,10 +128,15 @@ def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
         data = X.data if X.data.dtype == np.float32 else X.data.astype(np.float32)
         indices = X.indices if X.indices.dtype == np.int32 else X.indices.astype(np.int32)
         d_indptr = torch.from_numpy(indptr).to(dev, non_blocking=True)
-        # one bulk copy of values and indices (pinned when the caller provides pinned memory)
+        # one bulk copy of values and indices (asynchronous when the caller's arrays are in pinned memory)
         d_data = torch.from_numpy(np.ascontiguousarray(data)).to(dev, non_blocking=True)
         d_idx = torch.from_numpy(np.ascontiguousarray(indices)).to(dev, non_blocking=True)
-        L.csr_to_counts(ptr(d_data), ptr(d_idx), ptr(d_indptr), C_, 0, ptr(counts), ld, ptr(flags), st)
+        L.csr_to_counts(ptr(d_data), ptr(d_idx), ptr(d_indptr), C_, 0, G_, ptr(counts), ld, 0, ptr(flags), st)
+        if int(flags[3].item()):
+            # unsorted / duplicate indices: redo with summing stores (flags 0-2 are re-derived by the second pass)
+            counts.zero_()
+            flags.zero_()
+            L.csr_to_counts(ptr(d_data), ptr(d_idx), ptr(d_indptr), C_, 0, G_, ptr(counts), ld, 1, ptr(flags), st)
     else:
         Xh = np.asarray(X)
         if Xh.dtype == np.uint16 or Xh.dtype == np.int16:
@@ -130,12 +145,17 @@ def ingest_counts(X, device="cuda", rows_per_chunk: int = 8192) -> DeviceCounts:
                 counts.copy_(src, non_blocking=True)
             else:   # strided device-side placement of a straight (pinned-speed) upload
                 counts[:, :G_] = src.to(dev, non_blocking=True)
+            if Xh.dtype == np.int16:                              # the uint16 layout would read a negative as >= 32768
+                flags[4:5] = (counts.min() < 0).to(torch.int32)
         else:
-            for r0 in range(0, C_, rows_per_chunk):
-                blk = np.ascontiguousarray(Xh[r0:r0 + rows_per_chunk], dtype=np.float32)
+            # float32 C-order input is uploaded as is, block by block (no host conversion pass; asynchronous from pinned
+            # memory); other dtypes are converted block-wise on the host first
+            rows = max(1, min(rows_per_chunk, 65535))
+            for r0 in range(0, C_, rows):
+                blk = np.ascontiguousarray(Xh[r0:r0 + rows], dtype=np.float32)
                 d_blk = torch.from_numpy(blk).to(dev, non_blocking=True)
                 L.dense_to_counts(ptr(d_blk), G_, blk.shape[0], G_, r0, ptr(counts), ld, ptr(flags), st)
-    _check_flags(flags)
+    _check_flags(flags, comm)
     return DeviceCounts(counts, C_, G_)
 
 
@@ -177,10 +197,16 @@ class ResidualOperator:
         n_cells = counts.C
         if comm is not None:
             comm.all_reduce_sum(row_sum)
-        total = float(row_sum.sum().item())
+        # one read-back: [total, any all-zero gene, any all-zero cell]; the all-zero-gene test is rank-local on sharded
+        # input, so it is max-reduced - every rank must raise together or the others hang in the next collective
+        bad = torch.stack([(col_sum == 0).any(), (row_sum == 0).any()]).to(torch.int64)
+        if comm is not None:
+            comm.all_reduce_max(bad)
+        head = torch.cat([row_sum.sum().reshape(1), bad]).cpu().numpy()
+        total = float(head[0])
         if total <= 0:
             raise ValueError("count matrix is empty")
-        if bool((col_sum == 0).any().item()) or bool((row_sum == 0).any().item()):
+        if head[1] or head[2]:
             # the reference yields NaN residuals here (0/0) and sklearn PCA then raises on NaN input
             raise ValueError("Input contains all-zero genes or cells: Pearson residuals would be NaN. "
                              "Filter them first (the reference's loader uses min_cells=3).")

@@ -33,7 +33,7 @@ SIGNATURES = {
     "gc_profile_enable": (C.c_int, [C.c_int]),
     "gc_profile_collect": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "gc_fp64_probe": (C.c_int, [C.POINTER(C.c_double), _p, _p]),
-    "gc_csr_to_counts": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
+    "gc_csr_to_counts": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _i64, C.c_int, _p, _p]),
     "gc_dense_to_counts": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "gc_count_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "gc_pearson_residuals": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _f32, _f32, _f32, _p, _i64, _p]),

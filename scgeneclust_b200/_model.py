@@ -83,6 +83,10 @@ def scGeneClust(
     logger.opt(colors=True).info(f"GeneClust-{version} finished.")
     if return_info:
         from ._anndata_lite import DeviceMatrix
+        from .pp._preprocessing import STATE_KEY
+        # the device-side state (counts, residuals, PCA buffers, N x N redundancy) is not part of the reference's
+        # out-contract, cannot be pickled / written to h5ad and would pin gigabytes of HBM for the life of the result
+        copied_adata.uns.pop(STATE_KEY, None)
         if isinstance(copied_adata.X, DeviceMatrix):          # hand the residuals back as the ndarray the reference returns
             copied_adata.X = np.asarray(copied_adata.X)
         for slot in (copied_adata.varp, copied_adata.varm, copied_adata.obsm):

@@ -40,6 +40,15 @@ inline int check_launch(const char *kernel) {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute is per DEVICE: caches of "already configured" are indexed by the current device, so one process
+// (or thread) that drives several GPUs configures the kernel on each of them.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 // CUDA-event bracket around a dominant kernel (gc_profile_enable / gc_profile_collect); no-ops when disabled.
 enum ProfSlot { kProfRsvdPass = 0, kProfMiPairs = 1, kProfSlots = 2 };
 void prof_begin(int slot, cudaStream_t st);

@@ -19,17 +19,36 @@ __device__ __forceinline__ uint16_t to_count(float v, int32_t *flags) {
     return (uint16_t)v;
 }
 
+// flags: [0] value not a non-negative integer, [1] value (or sum of duplicates) above 65535, [2] column index outside
+// [0, G), [3] row not canonical (indices not strictly increasing: unsorted or duplicate entries).
+// ACCUMULATE = false: plain stores, valid for canonical rows only - a set flags[3] tells the caller to redo the block
+// with ACCUMULATE = true, where duplicates are summed like scipy's toarray() (scGeneClust/_model.py:124) by a 32-bit
+// atomic add on the word that holds the uint16.
+template <bool ACCUMULATE>
 __global__ void csr_to_counts_kernel(const float *__restrict__ data, const int32_t *__restrict__ indices,
-                                     const int64_t *__restrict__ indptr, int64_t n_rows, int64_t row0,
+                                     const int64_t *__restrict__ indptr, int64_t n_rows, int64_t row0, int64_t G,
                                      uint16_t *__restrict__ counts, int64_t ld, int32_t *flags) {
     // one warp per CSR row
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= n_rows) return;
     const int64_t base = indptr[0];
+    const int64_t e0 = indptr[r] - base, e1 = indptr[r + 1] - base;
     uint16_t *dst = counts + (row0 + r) * ld;
-    for (int64_t e = indptr[r] - base + lane; e < indptr[r + 1] - base; e += 32)
-        dst[indices[e]] = to_count(data[e], flags);
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        const int32_t col = indices[e];
+        if (col < 0 || col >= G) { flags[2] = 1; continue; }
+        const uint16_t v = to_count(data[e], flags);
+        if (!ACCUMULATE) {
+            if (e > e0 && indices[e - 1] >= col) flags[3] = 1;
+            dst[col] = v;
+        } else if (v) {
+            const int64_t pos = (row0 + r) * ld + col;                       // counts is 4-byte aligned, ld is even
+            const unsigned shift = (unsigned)(pos & 1) * 16u;
+            const unsigned old = atomicAdd(reinterpret_cast<unsigned int *>(counts) + (pos >> 1), (unsigned)v << shift);
+            if (((old >> shift) & 0xffffu) + v > 65535u) flags[1] = 1;
+        }
+    }
 }
 
 __global__ void dense_to_counts_kernel(const float *__restrict__ src, int64_t ld_src, int64_t n_rows, int64_t G,
@@ -459,11 +478,16 @@ __global__ void colabsmax_reduce_kernel(const float *__restrict__ cand_val, int6
 using namespace gc;
 
 extern "C" int gc_csr_to_counts(const float *data, const int32_t *indices, const int64_t *indptr, int64_t n_rows,
-                                int64_t row0, uint16_t *counts, int64_t ld, int32_t *flags, void *stream) {
+                                int64_t row0, int64_t G, uint16_t *counts, int64_t ld, int accumulate, int32_t *flags,
+                                void *stream) {
     GC_REQUIRE(data && indices && indptr && counts && flags, "null pointer");
+    GC_REQUIRE(G >= 1 && ld >= G && ld % 2 == 0 && ((uintptr_t)counts & 3) == 0, "bad counts layout");
     if (n_rows == 0) return 0;
-    csr_to_counts_kernel<<<(unsigned)ceil_div<int64_t>(n_rows * 32, 256), 256, 0, as_stream(stream)>>>(
-        data, indices, indptr, n_rows, row0, counts, ld, flags);
+    const unsigned grid = (unsigned)ceil_div<int64_t>(n_rows * 32, 256);
+    if (accumulate)
+        csr_to_counts_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(data, indices, indptr, n_rows, row0, G, counts, ld, flags);
+    else
+        csr_to_counts_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(data, indices, indptr, n_rows, row0, G, counts, ld, flags);
     return check_launch("csr_to_counts_kernel");
 }
 
@@ -512,8 +536,9 @@ extern "C" int gc_pearson_residuals(const uint16_t *counts, int64_t C, int64_t G
     return 0;
 }
 
-static thread_local double *g_col_partial = nullptr;
-static thread_local int64_t g_col_partial_cap = 0;
+// library-owned scratch of the column-sum pass, one buffer per (thread, device)
+static thread_local double *g_col_partial_dev[kMaxDevices] = {};
+static thread_local int64_t g_col_partial_cap_dev[kMaxDevices] = {};
 
 extern "C" int gc_residual_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, const float *row_sum_f,
                                 const float *col_sum_f, float total, float theta, float clip, double *zrow_sum,
@@ -528,6 +553,8 @@ extern "C" int gc_residual_sums(const uint16_t *counts, int64_t C, int64_t G, in
     }
     if (zcol_sum) {
         const int64_t need = (int64_t)kColSlabs * G;
+        double *&g_col_partial = g_col_partial_dev[current_device()];
+        int64_t &g_col_partial_cap = g_col_partial_cap_dev[current_device()];
         if (need > g_col_partial_cap) {
             if (g_col_partial) GC_CUDA(cudaFree(g_col_partial));
             GC_CUDA(cudaMalloc(&g_col_partial, sizeof(double) * need));

@@ -633,10 +633,11 @@ extern "C" int gc_kmeans_assign(const float *X, int64_t ldx, const int32_t *gath
     const int ds = d | 1;                                            // odd row stride: conflict-free lane-per-centre reads
     const size_t smem = (size_t)(K * ds + K) * sizeof(float);
     GC_REQUIRE(smem <= 200 * 1024, "K*d too large for the shared-memory centre cache");
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static thread_local size_t configured[kMaxDevices] = {};
+    const int dev_id = current_device();
+    if (smem > 48 * 1024 && smem > configured[dev_id]) {
         GC_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev_id] = smem;
     }
     // every CTA stages the centres once: a few samples per warp amortise that without starving the SMs
     const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(ceil_div<int64_t>(n, kAssignWarps), (int64_t)kNumSMs * 4));
@@ -652,10 +653,11 @@ extern "C" int gc_kmeans_minibatch_update(const float *X, int64_t ldx, const int
     GC_REQUIRE(d >= 1 && d <= kDMax && K >= 1 && n >= 1, "bad shape");
     const size_t hit_bytes = (size_t)n * 4;
     GC_REQUIRE(hit_bytes <= 200 * 1024, "mini-batch larger than 51200 samples");
-    static thread_local size_t upd_configured = 0;
-    if (hit_bytes > 48 * 1024 && hit_bytes > upd_configured) {
+    static thread_local size_t upd_configured[kMaxDevices] = {};
+    const int upd_dev = current_device();
+    if (hit_bytes > 48 * 1024 && hit_bytes > upd_configured[upd_dev]) {
         GC_CUDA(cudaFuncSetAttribute(kmeans_minibatch_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hit_bytes));
-        upd_configured = hit_bytes;
+        upd_configured[upd_dev] = hit_bytes;
     }
     kmeans_minibatch_update_kernel<<<K, 32, hit_bytes, as_stream(stream)>>>(X, ldx, gather, n, labels, centers_old,
                                                                       centers_new, weight_sums, K, d);

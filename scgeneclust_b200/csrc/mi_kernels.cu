@@ -645,10 +645,11 @@ extern "C" int gc_mi_cd(const double *XR, int64_t ldr, int64_t G, int n, const i
     static const bool force_brute = getenv("GC_MI_CD_BRUTE_FORCE") != nullptr;      // cross-check switch for the tests
     if (n <= 16384 && !force_brute) {
         const size_t smem = (size_t)np2 * 14;
-        static thread_local size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
+        static thread_local size_t configured[kMaxDevices] = {};
+        const int dev_id = current_device();
+        if (smem > 48 * 1024 && smem > configured[dev_id]) {
             GC_CUDA(cudaFuncSetAttribute(mi_cd_counts_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+            configured[dev_id] = smem;
         }
         mi_cd_counts_sorted_kernel<<<(unsigned)G, kCdThreads, smem, as_stream(stream)>>>(XR, ldr, G, n, np2, label, label_k,
                                                                                       n_label, m_all);

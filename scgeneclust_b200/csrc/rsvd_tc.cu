@@ -623,11 +623,12 @@ extern "C" int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G) {
 
 template <int TRANS, bool LO_CLIP>
 static int tc_launch(const TcArgs &a, dim3 grid, cudaStream_t st) {
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
         GC_CUDA(cudaFuncSetAttribute(rsvd_apply_tc_kernel<TRANS, LO_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TC_SMEM_BYTES));
-        configured = true;
+        configured[dev] = true;
     }
     rsvd_apply_tc_kernel<TRANS, LO_CLIP><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
     return 0;

@@ -188,10 +188,11 @@ extern "C" int gc_chol_inv(const double *Gm, int q, float *Rinv, int32_t *status
     GC_REQUIRE(Gm && Rinv && status, "null pointer");
     GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
     const int smem = 2 * kN * (kN + 1) * (int)sizeof(double);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local bool configured[kMaxDevices] = {};
+    const int dev_id = current_device();
+    if (!configured[dev_id]) {
         GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[dev_id] = true;
     }
     chol_inv_kernel<<<1, kCholThreads, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
     return check_launch("chol_inv_kernel");
@@ -201,10 +202,11 @@ extern "C" int gc_sym_eig(const double *Gm, int q, double *evals, float *U32, do
     GC_REQUIRE(Gm && evals && U32, "null pointer");
     GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
     const int smem = 2 * kN * (kN + 1) * (int)sizeof(double);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local bool configured[kMaxDevices] = {};
+    const int dev_id = current_device();
+    if (!configured[dev_id]) {
         GC_CUDA(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[dev_id] = true;
     }
     sym_eig_kernel<<<1, kEigThreads, smem, as_stream(stream)>>>(Gm, q, evals, U32, U64);
     return check_launch("sym_eig_kernel");

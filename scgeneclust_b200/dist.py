@@ -37,6 +37,12 @@ class GeneShardComm:
         self.world = dist.get_world_size(group)
         self.total_genes = int(total_genes)
         self.bounds = shard_bounds(self.total_genes, self.world)
+        if any(hi <= lo for lo, hi in self.bounds):
+            # shards are multiples of 64 genes: with fewer than 64 * (world - 1) + 1 genes a rank would hold nothing and
+            # its kernels would refuse the empty matrix while the other ranks wait in a collective.  Every rank computes
+            # the same bounds, so every rank raises here.
+            raise ValueError(f"{self.total_genes} genes cannot be split over {self.world} ranks in shards of 64: "
+                             f"use fewer ranks (at most {max(1, -(-self.total_genes // 64))})")
         self.gene_lo, self.gene_hi = self.bounds[self.rank]
 
     @property
@@ -47,6 +53,11 @@ class GeneShardComm:
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return t
 
     def absmax_merge(self, v: torch.Tensor) -> torch.Tensor:

@@ -210,14 +210,7 @@ def generate_gene_clusters(adata):
     g1, g2 = adata.uns['mst_edges'][:, 0], adata.uns['mst_edges'][:, 1]
     rel = adata.var['relevance'].values
     edge_min_relevance = np.minimum(rel[g1], rel[g2])
-    R = adata.varp['redundancy']
-    if hasattr(R, 'tensor'):                                  # device-backed: gather the N - 1 edge entries there
-        import torch as _torch
-        dev = R.tensor.device
-        edge_redundancy = R.tensor[_torch.from_numpy(np.asarray(g1, dtype=np.int64)).to(dev),
-                                   _torch.from_numpy(np.asarray(g2, dtype=np.int64)).to(dev)].cpu().numpy()
-    else:
-        edge_redundancy = R[g1, g2]
+    edge_redundancy = adata.varp['redundancy'][g1, g2]        # device-backed matrices gather the N - 1 entries there
     edge_scales = np.maximum(edge_min_relevance, adata.uns['mst_edges_complm']) / edge_redundancy
     MST = np.hstack((adata.uns['mst_edges'], edge_scales.reshape(-1, 1)))
     MST = MST[np.argsort(MST.T[2]), :]

@@ -1,5 +1,13 @@
-"""Gene-sharded (N ranks) vs single-GPU GeneClust-fast on the SAME matrix (developer / acceptance check, run under torchrun):
-PCA scores within 1e-3 relative per component, identical k-means labels and selected-gene list."""
+"""Gene-sharded (N ranks) vs single-GPU GeneClust-fast on the SAME matrix (acceptance check, run under torchrun; wrapped
+by tests/test_gpu_dist.py): PCA scores within 1e-3 relative per component, identical k-means labels and selected-gene
+list.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/check_sharded_parity.py [cells] [genes] [--backend nccl|gloo] [--same-device] [--csr]
+
+`--backend gloo --same-device` runs every rank on cuda:0 with gloo moving the (CUDA) tensors: the gene-sharded code
+path on a box with a single GPU (NCCL refuses two ranks on one device).  `--csr`: every rank ingests its shard from a
+host float32 CSR matrix (HostShard) instead of device-generated counts."""
 import os
 import sys
 
@@ -8,41 +16,53 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, ".")
-from scgeneclust_b200 import AnnDataLite, scGeneClust
+from scgeneclust_b200 import AnnDataLite, pp, scGeneClust, tl
+from scgeneclust_b200._device import HostShard
 from scgeneclust_b200.dist import GeneShardComm
 from scgeneclust_b200.synth import DeviceSynth, synth_params
 
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+backend = sys.argv[sys.argv.index("--backend") + 1] if "--backend" in sys.argv else "nccl"
+if "--backend" in sys.argv:
+    argv.remove(backend)
+same_device, use_csr = "--same-device" in sys.argv, "--csr" in sys.argv
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+local = 0 if same_device else local
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-C, G, K = int(sys.argv[1]) if len(sys.argv) > 1 else 20000, int(sys.argv[2]) if len(sys.argv) > 2 else 6000, 60
 dev = torch.device("cuda", local)
+if backend == "nccl":
+    dist.init_process_group("nccl", device_id=dev)
+else:
+    dist.init_process_group("gloo")
+C, G, K = int(argv[0]) if len(argv) > 0 else 20000, int(argv[1]) if len(argv) > 1 else 6000, 60
 comm = GeneShardComm(G)
 synth = DeviceSynth(synth_params(G, 0), dev)
 names = np.array([f"g{i}" for i in range(G)], dtype=object)
 shard = synth.counts(0, C, comm.gene_lo, comm.local_genes)
 shard.comm = comm
-info_s, sel_s = scGeneClust(AnnDataLite(shard, var_names=names), n_var_clusters=K, return_info=False, verbosity=0), None
-sel_s = info_s
-ok = True
-if rank == 0:
-    full = synth.counts(0, C, 0, G)
-    info, sel = scGeneClust(AnnDataLite(full, var_names=names), n_var_clusters=K, return_info=True, verbosity=0)
-# sharded run with return_info needs dense residuals (unsupported when sharded): compare through the stage state instead
-from scgeneclust_b200 import pp, tl
-from scgeneclust_b200.pp._preprocessing import get_state
+X_in = shard
+if use_csr:
+    import scipy.sparse as sp
+    X_in = HostShard(sp.csr_matrix(shard.to_numpy().astype(np.float32)), comm)
+sel_s = scGeneClust(AnnDataLite(X_in, var_names=names), n_var_clusters=K, verbosity=0)
+# the intermediate slots through the stage functions (return_info needs dense residuals: unsupported when sharded)
 ad = AnnDataLite(shard, var_names=names)
 pp.normalize(ad, 'sc')
 pp.reduce_dim(ad, 'fast', 0)
 tl.cluster_genes(ad, None, 'fast', n_gene_clusters=K, random_state=0)
+ok = True
 if rank == 0:
+    full = synth.counts(0, C, 0, G)
+    info, sel = scGeneClust(AnnDataLite(full, var_names=names), n_var_clusters=K, return_info=True, verbosity=0)
     e_s, e_1 = ad.varm['X_pca'], info.varm['X_pca']
     rel = np.linalg.norm(e_s - e_1, axis=0) / np.linalg.norm(e_1, axis=0)
     same_labels = np.array_equal(ad.var['cluster'].to_numpy(), info.var['cluster'].to_numpy())
     same_sel = np.array_equal(sel_s, sel)
-    print(f"world {world}: PCA rel err max {rel.max():.2e} (first 10 PCs {rel[:10].max():.2e}), labels identical {same_labels}, "
-          f"selected list identical {same_sel} ({len(sel)} genes)")
-    ok = rel.max() <= 1e-3 and same_sel
+    print(f"world {world} ({backend}): PCA rel err max {rel.max():.2e} (first 10 PCs {rel[:10].max():.2e}), labels "
+          f"identical {same_labels}, selected list identical {same_sel} ({len(sel)} genes)", flush=True)
+    ok = bool(rel.max() <= 1e-3 and same_labels and same_sel)
+flag = torch.tensor([int(ok)], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.exit(0 if int(flag.item()) else 1)

@@ -116,3 +116,80 @@ def test_c4_redundancy_sampled_pairs_and_structure(torch_cuda):
     YR = np.stack([mb.prep_target(E[j], xi2) for j in pairs[:, 1]])
     _, _, mi_o = mb.ksg_batch(XR, YR, np.stack([np.arange(len(pairs))] * 2, 1))
     assert np.array_equal(D.cpu().numpy()[pairs[:, 0], pairs[:, 1]], mi_o)
+
+
+def test_c3_pass_kernel_sampled_blocks_vs_oracle(torch_cuda, c3_operator):
+    """The tcgen05 pass kernel at the benchmarked size against the ORACLE (not against another kernel of this repo):
+    for blocks of 64 cells (M Q) and blocks of 64 genes (M^T Q) the counts are regenerated on the CPU by the oracle's
+    generator, turned into Pearson residuals by the oracle's formula (float32, like the reference) from the exact
+    integer sums, centred, and multiplied with the panel in float64.  Tolerance 2e-4 of the output scale: the bf16
+    hi+lo operand split (2^-16 per product) plus float32 accumulation over 20 000 / 50 000 terms."""
+    torch = torch_cuda
+    from oracle import stages
+    from oracle import synth as osy
+    params, counts, op = c3_operator
+    po = osy.synth_params(G3, 0)
+    dev = op.counts.device
+    g = torch.Generator(device="cpu").manual_seed(7)
+    Q = torch.zeros((G3, 64)); Q[:, :60] = torch.randn((G3, 60), generator=g)
+    W = torch.zeros((C3, 64)); W[:, :60] = torch.randn((C3, 60), generator=g)
+    zr, _ = op.residual_sums(rows=True, cols=False)
+    shift = (zr / G3).to(torch.float32)
+    Y = op.apply(0, Q.to(dev), shift, None).cpu().numpy().astype(np.float64)
+    Zt = op.apply(1, W.to(dev), shift, None).cpu().numpy().astype(np.float64)
+    row_sum = op.row_sum.cpu().numpy().astype(np.float64)
+    col_sum = op.col_sum.cpu().numpy().astype(np.float64)
+    total = float(op.total)
+    shift_h = shift.cpu().numpy().astype(np.float64)
+    Qh, Wh = Q.numpy().astype(np.float64), W.numpy().astype(np.float64)
+    y_scale, z_scale = np.abs(Y).max(), np.abs(Zt).max()
+    worst_y = worst_z = worst_shift = 0.0
+    for c0 in (0, 12_345, 31_000, C3 - 64):                      # incl. the ragged last tile (50 000 = 390 x 128 + 80)
+        blk = osy.synth_counts_c(po, c0, 64, 0, G3)
+        Z = stages.pearson_residuals_block(blk, row_sum[c0:c0 + 64], col_sum, total, C3).astype(np.float64)
+        ref_shift = Z.mean(axis=1)
+        worst_shift = max(worst_shift, np.abs(ref_shift - shift_h[c0:c0 + 64]).max())
+        ref = (Z - ref_shift[:, None]) @ Qh
+        worst_y = max(worst_y, np.abs(ref - Y[c0:c0 + 64]).max())
+    for g0 in (0, 7_777, 13_120, G3 - 64):
+        blk = osy.synth_counts_c(po, 0, C3, g0, 64)
+        Z = stages.pearson_residuals_block(blk, row_sum, col_sum[g0:g0 + 64], total, C3).astype(np.float64)
+        ref = (Z - shift_h[:, None]).T @ Wh
+        worst_z = max(worst_z, np.abs(ref - Zt[g0:g0 + 64]).max())
+    print(f"c3 sampled blocks vs oracle: M Q {worst_y / y_scale:.2e}, M^T Q {worst_z / z_scale:.2e} of scale; "
+          f"centring vector abs err {worst_shift:.2e}")
+    assert worst_shift <= 1e-5
+    assert worst_y <= 2e-4 * y_scale
+    assert worst_z <= 2e-4 * z_scale
+
+
+def test_c3_fast_selection_vs_oracle_golden(torch_cuda, c3_operator, golden_dir):
+    """GeneClust-fast at config c3 (50 000 x 20 000, K = 200) through the entry point against the CPU oracle's result on
+    the SAME matrix (tests/golden/c3_fast_oracle.npz, written by tests/golden/make_c3_oracle.py: oracle/stages.py =
+    numpy residuals + sklearn 1.9.0 PCA / MiniBatchKMeans / IsolationForest; 47 s on 8 cores).  north_star's bars: PCA
+    scores within 1e-3 relative per component, gene clusters reported as ARI - and, where the float32 paths agree
+    closely enough, the same labels and the same selected-gene list."""
+    import os
+    from sklearn.metrics import adjusted_rand_score
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    _, counts, _ = c3_operator
+    gold = np.load(os.path.join(golden_dir, "c3_fast_oracle.npz"), allow_pickle=False)
+    names = np.array([f"g{i}" for i in range(G3)], dtype=object)
+    sel = scGeneClust(AnnDataLite(counts, var_names=names), n_var_clusters=200, version='fast', verbosity=0)
+    # the intermediate slots through the stage functions (return_info=True would materialise 4 GB of residuals)
+    from scgeneclust_b200 import pp, tl
+    ad = AnnDataLite(counts, var_names=names)
+    pp.normalize(ad, 'sc')
+    pp.reduce_dim(ad, 'fast', 0)
+    tl.cluster_genes(ad, None, 'fast', n_gene_clusters=200, random_state=0)
+    emb = ad.varm['X_pca']
+    rel = np.linalg.norm(emb - gold['X_pca'], axis=0) / np.linalg.norm(gold['X_pca'], axis=0)
+    labels = ad.var['cluster'].to_numpy()
+    ari = adjusted_rand_score(labels, gold['labels'])
+    same_labels = np.array_equal(labels, gold['labels'])
+    same_list = np.array_equal(sel.astype(str), gold['selected'])
+    print(f"c3 vs oracle golden: PCA rel err max {rel.max():.2e}, ARI {ari:.4f}, labels identical {same_labels}, "
+          f"selected list identical {same_list} ({len(sel)} vs {len(gold['selected'])} genes)")
+    assert rel.max() <= 1e-3
+    assert ari >= 0.9
+    assert same_labels and same_list
