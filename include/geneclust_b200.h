@@ -100,8 +100,13 @@ typedef struct {
 int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G);
 int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *partials,
                   void *stream);
+/* The previous tensor-core implementation of the same pass (both operands from shared memory, "SS mode"; gc_rsvd_apply
+ * keeps the residual operand in tensor memory and feeds the count tiles by TMA): kept for A/B timing and as a second
+ * tcgen05 implementation the tests compare with. */
+int gc_rsvd_apply_ss(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *partials,
+                     void *stream);
 /* The SIMT (FFMA, exact float32 products) implementation of the same pass; kept as the on-device cross-check of
- * the tensor-core kernel. */
+ * the tensor-core kernels. */
 int gc_rsvd_apply_simt(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *partials,
                        void *stream);
 /* The test matrix Omega of the randomized solver, drawn on the device exactly as scikit-learn draws it on the host

@@ -223,14 +223,18 @@ class ResidualOperator:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.counts.device)
         return self._scratch
 
-    def apply(self, trans: int, Q: torch.Tensor, row_shift=None, col_shift=None, out=None, simt: bool = False):
-        """trans=0: (C x 64) = M @ Q(G x 64);  trans=1: (G x 64) = M^T @ Q(C x 64)."""
+    def apply(self, trans: int, Q: torch.Tensor, row_shift=None, col_shift=None, out=None, simt: bool = False,
+              kernel: Optional[str] = None):
+        """trans=0: (C x 64) = M @ Q(G x 64);  trans=1: (G x 64) = M^T @ Q(C x 64).
+        kernel: 'ts' (default; tcgen05 with the residual operand in tensor memory), 'ss' (tcgen05, both operands from
+        shared memory) or 'simt' (exact float32 FFMA) - the last two are cross-checks."""
         n_in, n_out = (self.G, self.C) if trans == 0 else (self.C, self.G)
         assert Q.shape == (n_in, Q_LD) and Q.dtype == torch.float32
         if out is None:
             out = torch.empty((n_out, Q_LD), dtype=torch.float32, device=Q.device)
         m = self.struct(row_shift, col_shift)
-        fn = lib().rsvd_apply_simt if simt else lib().rsvd_apply
+        kernel = kernel or ('simt' if simt else 'ts')
+        fn = {'ts': lib().rsvd_apply, 'ss': lib().rsvd_apply_ss, 'simt': lib().rsvd_apply_simt}[kernel]
         fn(C.byref(m), trans, ptr(Q), ptr(out), Q_LD, ptr(self._scratch_buf()), stream_handle())
         return out
 
@@ -386,8 +390,56 @@ def _small_pca(op: ResidualOperator, samples: str, solver: str, n_comps: int) ->
     return scores.to(torch.float32).contiguous()
 
 
+@dataclass
+class PcaPlan:
+    """What sklearn's PCA(svd_solver='auto') + randomized_svd will do for this shape (decomposition/_pca.py:524-536,
+    utils/extmath.py:313-386) - known from the shape alone, before any data is touched."""
+    solver: str
+    n_comps: int
+    q: int
+    n_iter: int
+    transpose: bool
+    omega_rows: int            # A.shape[1] after sklearn's transposition = rows of the test matrix Omega
+
+
+def plan_pca(n_cells: int, n_genes_total: int, samples: str, n_comps: Optional[int] = None) -> PcaPlan:
+    n_samples, n_features = (n_genes_total, n_cells) if samples == "genes" else (n_cells, n_genes_total)
+    min_dim = min(n_samples, n_features)
+    if n_comps is None:
+        n_comps = min_dim - 1 if N_PCS >= min_dim else N_PCS     # scanpy's n_comps rule
+    solver = pca_solver(n_samples, n_features, n_comps)
+    n_iter = 7 if n_comps < 0.1 * min_dim else 4
+    transpose = n_samples < n_features
+    # A (after sklearn's transpose) has the stored cells x genes orientation iff ...
+    a_is_stored = transpose if samples == "genes" else (not transpose)
+    return PcaPlan(solver, n_comps, n_comps + N_OVERSAMPLES, n_iter, transpose, n_genes_total if a_is_stored else n_cells)
+
+
+@dataclass
+class OmegaPrefetch:
+    """An Omega panel being generated on the side stream (see `prefetch_omega`)."""
+    key: tuple
+    panel: torch.Tensor
+    status: torch.Tensor
+    stream: "torch.cuda.Stream"
+
+
+def prefetch_omega(random_state: int, plan: PcaPlan, device) -> Optional[OmegaPrefetch]:
+    """Start generating the solver's test matrix on the side stream NOW (the entry point calls this before the counts are
+    even uploaded): the MT19937 word stream comes from one CTA, so it is the one piece of the PCA worth starting early."""
+    if plan.solver != "randomized" or plan.q > Q_LD:
+        return None
+    dev = torch.device(device)
+    main_stream = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main_stream)
+    with torch.cuda.stream(side):
+        panel = device_normal_panel(random_state, plan.omega_rows, plan.q, dev)
+    return OmegaPrefetch((int(random_state), plan.omega_rows, plan.q), panel, panel._gc_status, side)
+
+
 def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_comps: Optional[int] = None,
-                   simt: bool = False, info: Optional[dict] = None) -> torch.Tensor:
+                   simt: bool = False, info: Optional[dict] = None, omega: Optional[OmegaPrefetch] = None) -> torch.Tensor:
     """PCA scores (n_samples x n_comps, float32, device) of the residual matrix.
 
     samples='genes' is `sc.pp.pca(norm_counts.T)` (scGeneClust/pp/_preprocessing.py:52): samples are genes,
@@ -395,16 +447,14 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     Follows sklearn's randomized solver step for step (same Omega, n_iter rule, transpose rule, v-based sign
     flip); the LU/QR panel normalisers are replaced by Cholesky-QR, which spans the same subspace.
     With `comm` (gene-sharded operator) panels in cell space are all-reduced and panels in gene space stay local.
+    `omega`: a test matrix already being generated (`prefetch_omega`); used if it was made for the same draw.
     """
     L, st = lib(), stream_handle()
     dev = op.counts.device
     comm = op.counts.comm
     G_total = op.G if comm is None else comm.total_genes
-    n_samples, n_features = (G_total, op.C) if samples == "genes" else (op.C, G_total)
-    min_dim = min(n_samples, n_features)
-    if n_comps is None:
-        n_comps = min_dim - 1 if N_PCS >= min_dim else N_PCS     # scanpy's n_comps rule
-    solver = pca_solver(n_samples, n_features, n_comps)
+    plan = plan_pca(op.C, G_total, samples, n_comps)
+    n_comps, solver, q, n_iter, transpose = plan.n_comps, plan.solver, plan.q, plan.n_iter, plan.transpose
     if solver != "randomized":
         if comm is not None:
             raise NotImplementedError(f"PCA solver '{solver}' (small matrices) is not available on gene-sharded input")
@@ -412,42 +462,37 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         if info is not None:
             info.update(solver=solver, n_comps=n_comps, passes=0)
         return scores
-    q = n_comps + N_OVERSAMPLES
     if q > Q_LD:
         raise NotImplementedError("n_components + 10 must be <= 64")
-    n_iter = 7 if n_comps < 0.1 * min_dim else 4
-    transpose = n_samples < n_features
 
-    fwd_is_stored = transpose if samples == "genes" else (not transpose)
-    n_in_total_early = G_total if fwd_is_stored else op.C
     # Omega exactly as sklearn draws it (utils/extmath.py:323-334): normal((A.shape[1], q)) cast to float32 - the
     # legacy RandomState stream is reproduced on the device from the seeded MT19937 state (20-40 ms on the host).
-    # Its word stream comes from ONE CTA (MT19937 is sequential), so it runs on a side stream underneath the
-    # residual-sum pass over the count matrix.
+    # Its word stream comes from ONE CTA (MT19937 is sequential), so it runs on a side stream.
     main_stream = torch.cuda.current_stream()
-    side_stream = _side_stream(dev)
-    side_stream.wait_stream(main_stream)
-    with torch.cuda.stream(side_stream):
-        Qp_full = device_normal_panel(random_state, n_in_total_early, q, dev)
-    omega_status = Qp_full._gc_status
+    if omega is None or omega.key != (int(random_state), plan.omega_rows, q):
+        omega = prefetch_omega(random_state, plan, dev)
+    Qp_full, omega_status, side_stream = omega.panel, omega.status, omega.stream
 
-    # centring vector = mean over samples of every feature (decomposition/_pca.py:733-735)
-    if samples == "genes":
-        zr, _ = op.residual_sums(rows=True, cols=False)
-        if comm is not None:
-            comm.all_reduce_sum(zr)
-        row_shift, col_shift = (zr / float(G_total)).to(torch.float32), None
-        a_is_stored = transpose            # A (after sklearn's transpose) has the stored cells x genes orientation
-    else:
-        _, zc = op.residual_sums(rows=False, cols=True)
-        row_shift, col_shift = None, (zc / float(op.C)).to(torch.float32)
-        a_is_stored = not transpose
-    fwd = 0 if a_is_stored else 1          # trans flag of  A @ Q
+    a_is_stored = transpose if samples == "genes" else (not transpose)
+    fwd = 0 if a_is_stored else 1          # trans flag of  A @ Q ; trans=0 contracts genes, trans=1 contracts cells
     bwd = 1 - fwd
-    # A.shape[1] = length of the Omega rows; trans=0 contracts genes, trans=1 contracts cells
-    n_in_total = G_total if fwd == 0 else op.C
+    # centring vector = mean over samples of every feature (decomposition/_pca.py:733-735).  It is indexed by cells for
+    # samples='genes' (row_shift) and by genes for samples='cells' (col_shift).  When sklearn transposes, that is the
+    # OUTPUT index of the first pass, and the sums come out of that pass for free: Omega gets a column of ones in a
+    # padding slot, so column 63 of the raw product is  Z 1  (resp. Z^T 1); the rank-1 centring term is then applied
+    # to the result.  Otherwise the shift is needed INSIDE the first pass and costs one extra pass over the counts.
+    ones_trick = transpose and q < Q_LD
+    row_shift = col_shift = None
+    if not ones_trick:
+        if samples == "genes":
+            zr, _ = op.residual_sums(rows=True, cols=False)
+            if comm is not None:
+                comm.all_reduce_sum(zr)
+            row_shift = (zr / float(G_total)).to(torch.float32)
+        else:
+            _, zc = op.residual_sums(rows=False, cols=True)
+            col_shift = (zc / float(op.C)).to(torch.float32)
 
-    assert n_in_total == n_in_total_early
     main_stream.wait_stream(side_stream)
     Qp_full.record_stream(main_stream)
     omega_status.record_stream(main_stream)
@@ -474,8 +519,29 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         return alg.chol_qr(Y, q, dst, comm, replicated=(trans == 0))
 
     Qcur = Qp
-    for _ in range(n_iter):
-        Qcur = normalise(fwd, apply(fwd, Qcur))
+    for it in range(n_iter):
+        if it == 0 and ones_trick:
+            # raw first pass with the ones column; row n_out of `ext` carries the column sums of Omega so that one
+            # all-reduce (gene-sharded, trans 0) covers both
+            n_out = op.C if fwd == 0 else op.G
+            n_k_total = G_total if fwd == 0 else op.C
+            ext = torch.empty((n_out + 1, Q_LD), dtype=torch.float32, device=dev)
+            Qp[:, Q_LD - 1] = 1.0
+            op.apply(fwd, Qp, None, None, out=ext[:n_out], simt=simt)
+            ext[n_out] = Qp.sum(dim=0, dtype=torch.float64).to(torch.float32)
+            if comm is not None and fwd == 0:
+                comm.all_reduce_sum(ext)
+            shift = (ext[:n_out, Q_LD - 1] / float(n_k_total)).contiguous()
+            Y = tmp_c if fwd == 0 else tmp_g
+            torch.addcmul(ext[:n_out], shift.unsqueeze(1), ext[n_out].unsqueeze(0), value=-1.0, out=Y)
+            Y[:, q:] = 0.0
+            if samples == "genes":
+                row_shift = shift
+            else:
+                col_shift = shift
+            Qcur = normalise(fwd, Y)
+        else:
+            Qcur = normalise(fwd, apply(fwd, Qcur))
         Qcur = normalise(bwd, apply(bwd, Qcur))
     # final range: orthonormal basis by two Cholesky-QR steps (qr_normalizer of extmath.py:386)
     Y = apply(fwd, Qcur)

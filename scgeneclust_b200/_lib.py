@@ -40,6 +40,7 @@ SIGNATURES = {
     "gc_residual_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _f32, _f32, _f32, _p, _p, _p]),
     "gc_rsvd_scratch_bytes": (_i64, [_i64, _i64]),
     "gc_rsvd_apply": (C.c_int, [C.POINTER(ResidualMatrix), C.c_int, _p, _p, C.c_int, _p, _p]),
+    "gc_rsvd_apply_ss": (C.c_int, [C.POINTER(ResidualMatrix), C.c_int, _p, _p, C.c_int, _p, _p]),
     "gc_rsvd_apply_simt": (C.c_int, [C.POINTER(ResidualMatrix), C.c_int, _p, _p, C.c_int, _p, _p]),
     "gc_mt19937_normal_scratch_bytes": (_i64, [_i64, C.c_int]),
     "gc_mt19937_normal_panel": (C.c_int, [_p, C.c_int, _i64, C.c_int, _p, C.c_int, _p, _p, _p]),

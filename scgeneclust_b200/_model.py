@@ -65,6 +65,9 @@ def scGeneClust(
     )
     copied_adata = _working_copy(raw_adata)
 
+    # head start for the gene PCA: its Omega test matrix is a sequential MT19937 stream (one CTA), so it is started on a
+    # side stream before the counts are uploaded and summed
+    pp.start_omega(copied_adata, random_state)
     # preprocessing: residuals stay an implicit device operator for `fast`; `ps` and `return_info` need them dense
     pp.normalize(copied_adata, modality, materialize=(version == 'ps' or return_info))
     pp.reduce_dim(copied_adata, version, random_state)

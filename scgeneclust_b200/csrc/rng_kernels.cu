@@ -18,10 +18,6 @@ namespace gc {
 constexpr int kMtN = 624, kMtM = 397;
 constexpr int kAttemptsPerCta = 2048;    // 256 threads x 8 attempts
 
-__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
-    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-}
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= y >> 11;
     y ^= (y << 7) & 0x9d2c5680u;
@@ -30,11 +26,23 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
+// the twist term of the recurrence  x[k + 624] = x[k + 397] ^ tw(x[k], x[k + 1])
+__device__ __forceinline__ uint32_t mt_tw(uint32_t cur, uint32_t nxt) {
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
 // One CTA: emits n_words tempered outputs starting at position `pos` (0..624; 624 = regenerate first) of `state`.
-// The 624-word block is regenerated in three dependent phases ([0,227), [227,454), [454,624)) into the other of two
-// buffers (old values are read from the current one, so a phase needs no read/write fence of its own): three
-// __syncthreads per 624 words, and every thread tempers and stores the word it has just produced.
-__global__ void __launch_bounds__(256)
+// A 624-word block is regenerated from the PREVIOUS block alone, all 624 words in parallel, one __syncthreads per block
+// (the textbook in-place loop needs three dependent phases: words [227, 454) read new words [0, 227), words [454, 624)
+// read new words [227, 397)).  Substituting the recurrence into itself removes the dependence on new words:
+//   new[i] = old[i + 397]                                                                 ^ tw(old[i], old[i + 1])   i < 227
+//   new[i] = old[i + 170] ^ tw(old[i - 227], old[i - 226])                                ^ tw(old[i], old[i + 1])   227 <= i < 454
+//   new[i] = old[i -  57] ^ tw(old[i - 454], old[i - 453]) ^ tw(old[i - 227], old[i - 226]) ^ tw(old[i], old[i + 1]) 454 <= i
+// (for i = 623 the last argument is new[0] = old[397] ^ tw(old[0], old[1]), recomputed by that thread).  Checked word
+// for word against numpy's stream (tests/test_gpu_embed.py compares the normals drawn from it).
+constexpr int kMtThreads = 640;
+__global__ void __launch_bounds__(kMtThreads)
 mt19937_stream_kernel(const uint32_t *__restrict__ state, int pos, int64_t n_words, uint32_t *__restrict__ out) {
     __shared__ uint32_t buf[2][kMtN];
     const int t = threadIdx.x;
@@ -51,23 +59,18 @@ mt19937_stream_kernel(const uint32_t *__restrict__ state, int pos, int64_t n_wor
         const uint32_t *mt = buf[cur];
         uint32_t *nt = buf[cur ^ 1];
         const int64_t left = n_words - done;
-        if (t < 227) {
-            const uint32_t v = mt_twist(mt[t], mt[t + 1], mt[t + kMtM]);
+        if (t < kMtN) {
+            uint32_t v;
+            if (t < 227) {
+                v = mt[t + kMtM] ^ mt_tw(mt[t], mt[t + 1]);
+            } else if (t < 454) {
+                v = mt[t + 170] ^ mt_tw(mt[t - 227], mt[t - 226]) ^ mt_tw(mt[t], mt[t + 1]);
+            } else {
+                const uint32_t nxt = t < kMtN - 1 ? mt[t + 1] : (mt[kMtM] ^ mt_tw(mt[0], mt[1]));
+                v = mt[t - 57] ^ mt_tw(mt[t - 454], mt[t - 453]) ^ mt_tw(mt[t - 227], mt[t - 226]) ^ mt_tw(mt[t], nxt);
+            }
             nt[t] = v;
             if (t < left) out[done + t] = mt_temper(v);
-        }
-        __syncthreads();
-        if (t < 227) {
-            const uint32_t v = mt_twist(mt[t + 227], mt[t + 228], nt[t]);
-            nt[t + 227] = v;
-            if (t + 227 < left) out[done + t + 227] = mt_temper(v);
-        }
-        __syncthreads();
-        if (t < 170) {         // kk = 454 + t; the last word (kk = 623) wraps to the NEW word 0
-            const uint32_t nxt = t < 169 ? mt[t + 455] : nt[0];
-            const uint32_t v = mt_twist(mt[t + 454], nxt, nt[t + 227]);
-            nt[t + 454] = v;
-            if (t + 454 < left) out[done + t + 454] = mt_temper(v);
         }
         __syncthreads();
         done += min((int64_t)kMtN, left);
@@ -191,7 +194,7 @@ extern "C" int gc_mt19937_normal_panel(const uint32_t *mt_state, int mt_pos, int
     uint32_t *words = (uint32_t *)p;      p += rng_align(att * 16);
     int32_t *cta_count = (int32_t *)p;    p += rng_align(n_cta * 4);
     int64_t *cta_offset = (int64_t *)p;
-    mt19937_stream_kernel<<<1, 256, 0, st>>>(mt_state, mt_pos, att * 4, words);
+    mt19937_stream_kernel<<<1, kMtThreads, 0, st>>>(mt_state, mt_pos, att * 4, words);
     if (int rc = check_launch("mt19937_stream_kernel")) return rc;
     polar_count_kernel<<<(unsigned)n_cta, 256, 0, st>>>(words, att, cta_count);
     if (int rc = check_launch("polar_count_kernel")) return rc;

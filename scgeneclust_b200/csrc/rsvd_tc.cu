@@ -28,6 +28,8 @@
 // Bound: HBM (algorithmic 2 B/entry); the producer ALU work (12 lane-instructions per entry) is the practical limiter.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gc {
@@ -569,6 +571,8 @@ __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_
 // (less partial traffic).  50 000 x 20 000: 3 slabs for M Q (8 waves), 13 for M^T Q; with the genes sharded 8 ways
 // (400 000 x 2 500 per GPU) M Q runs unsplit instead of doubling the CTA count for 2 % better wave filling.
 __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
+    static const int forced = []() { const char *e = getenv("GC_RSVD_SPLIT"); return e ? atoi(e) : 0; }();   // developer knob
+    if (forced > 0) return forced;
     const int64_t slots = (int64_t)kNumSMs;
     int best = 1;
     int64_t best_cost = 0;
@@ -582,6 +586,8 @@ __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
 }
 
 }  // namespace gc
+
+#include "rsvd_ts.cuh"
 
 using namespace gc;
 
@@ -634,8 +640,9 @@ static int tc_launch(const TcArgs &a, dim3 grid, cudaStream_t st) {
     return 0;
 }
 
-extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *scratch,
-                             void *stream) {
+// mode 0: TS kernel (product path), 1: SS kernel
+static int rsvd_apply_impl(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *scratch,
+                           void *stream, int mode) {
     GC_REQUIRE(M && Qin && Y && scratch, "null pointer");
     GC_REQUIRE(M->counts != nullptr && M->C >= 1 && M->G >= 1, "empty matrix");
     GC_REQUIRE(M->ld >= M->G && M->ld % 8 == 0 && ((uintptr_t)M->counts & 15) == 0, "counts: ld % 8 == 0, 16-byte aligned");
@@ -670,15 +677,39 @@ extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float
     GC_REQUIRE(M->C < (1ll << 31), "more than 2^31 cells");
     dim3 grid((unsigned)n_tiles, (unsigned)a.n_split);
     const bool lo_clip = !(M->clip * M->clip >= M->theta);     // z > -sqrt(theta) always: lower clip is dead otherwise
-    prof_begin(kProfRsvdPass, st);
+    // kernel choice: the TS-mode kernel (A operand in tensor memory, TMA-fed count tiles) is the product path; the
+    // SS-mode kernel stays reachable (gc_rsvd_apply_ss, or GC_RSVD_MODE=ss for a whole run) as the cross-check of the
+    // tests and for A/B timing
+    static const bool force_ss = []() { const char *e = getenv("GC_RSVD_MODE"); return e && strcmp(e, "ss") == 0; }();
     int rc;
-    if (trans == 0) rc = lo_clip ? tc_launch<0, true>(a, grid, st) : tc_launch<0, false>(a, grid, st);
-    else rc = lo_clip ? tc_launch<1, true>(a, grid, st) : tc_launch<1, false>(a, grid, st);
-    prof_end(kProfRsvdPass, st);
+    if (mode == 1 || force_ss) {
+        prof_begin(kProfRsvdPass, st);
+        if (trans == 0) rc = lo_clip ? tc_launch<0, true>(a, grid, st) : tc_launch<0, false>(a, grid, st);
+        else rc = lo_clip ? tc_launch<1, true>(a, grid, st) : tc_launch<1, false>(a, grid, st);
+        prof_end(kProfRsvdPass, st);
+    } else {
+        GC_REQUIRE(M->ld < (1ll << 31), "leading dimension too large for the tensor map coordinates");
+        CUtensorMap map;
+        if (int rcm = make_counts_tensor_map(&map, M->counts, M->C, M->ld, trans)) return rcm;
+        prof_begin(kProfRsvdPass, st);
+        if (trans == 0) rc = lo_clip ? ts_launch<0, true>(map, a, grid, st) : ts_launch<0, false>(map, a, grid, st);
+        else rc = lo_clip ? ts_launch<1, true>(map, a, grid, st) : ts_launch<1, false>(map, a, grid, st);
+        prof_end(kProfRsvdPass, st);
+    }
     if (rc) return rc;
     if (int rc2 = check_launch("rsvd_apply_tc_kernel")) return rc2;
     const int64_t o4 = a.n_out * TC_TN / 4;
     rsvd_tc_reduce_kernel<<<(unsigned)ceil_div<int64_t>(o4, 256), 256, 0, st>>>(a.partials, o4, a.n_split, out_shift,
                                                                                s.colsum, Y);
     return check_launch("rsvd_tc_reduce_kernel");
+}
+
+extern "C" int gc_rsvd_apply(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *scratch,
+                             void *stream) {
+    return rsvd_apply_impl(M, trans, Qin, Y, q, scratch, stream, 0);
+}
+
+extern "C" int gc_rsvd_apply_ss(const gc_residual_matrix *M, int trans, const float *Qin, float *Y, int q, void *scratch,
+                                void *stream) {
+    return rsvd_apply_impl(M, trans, Qin, Y, q, scratch, stream, 1);
 }

@@ -1,0 +1,374 @@
+// Randomized-SVD pass, version 4: the A operand (the Pearson-residual tile) lives in TENSOR MEMORY (tcgen05.mma with
+// A from TMEM, "TS mode"), the raw uint16 count tiles arrive through a TMA-fed shared-memory ring.
+// Included by rsvd_tc.cu (shares its PTX wrappers, the prep / column-sum / reduce kernels and the scratch layout).
+//
+// Why: the SS-mode kernel above moves 88 KB through shared memory per 128 x 64 stage (32 KB of
+// A hi/lo written by the producers, 56 KB fetched by the UMMAs) and its producers spend ~1/3 of their instructions on
+// global-load address arithmetic, bounds clamps and shared-memory stores.  Here
+//   * one elected thread issues ONE tensor-map TMA per stage for the 16 KB raw count tile (zero fill outside the matrix,
+//     so there is no bounds code at all) + bulk copies of the stage's 64 per-k constants and of the panel tile;
+//   * a producer thread owns one output row of the tile (= its TMEM lane): it reads the row's counts from shared memory
+//     (M Q: eight swizzled LDS.128; M^T Q: 64 conflict-free LDS.U16 down a column of the tile), forms the residuals in
+//     registers, splits them into bf16 hi + lo and writes both straight into TMEM with tcgen05.st (256 B/clk);
+//   * the tensor core reads A from TMEM and only the panel tile [Q_hi | Q_lo] from shared memory (24 KB per stage), and an
+//     A-in-TMEM M128 x N64 UMMA runs at its 32-cycle floor (48 in SS mode);
+//   * BOTH pass directions use the same kernel - the direction only changes how the raw tile is read.
+// Accumulators: D1 (128 columns) += A_hi [Q_hi | Q_lo] (one N = 128 UMMA), D2 (64 columns) += A_lo Q_hi; the epilogue adds
+// the three partial results.  The small A_lo Q_hi products get their OWN accumulator: the tensor core's fp32 accumulate
+// truncates, so adding them into the large hi.hi sums (tried: 128 accumulator columns, 6 stages) loses them - the PCA
+// scores moved from 8e-5 to 8e-4 of the oracle's.  TMEM: 192 accumulator columns + 5 A stages x 64 columns (hi: 32
+// columns = 64 bf16, lo: 32) = 512.
+//
+// CTA = one 128-row output tile x one k-slab, 22 warps:
+//   warps 0-19  producers, five groups of four warps (warp w of a group owns TMEM lanes 32 (w % 4) .. +31); group g owns the
+//               stages it = g, g + 5, ... and TMEM A slot g;  the first 16 also run the epilogue
+//   warp 20     MMA issuer + TMEM owner
+//   warp 21     TMA issuer of the raw count tiles + per-k constants (nine tiles in flight: the ring is deeper than the
+//               number of groups, so a group's next tile is already in shared memory when it finishes the current one)
+//   warp 22     bulk-copy issuer of the panel tiles
+#pragma once
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
+
+namespace gc {
+
+constexpr int TS_GROUPS = 5;
+constexpr int TS_PRODUCER_WARPS = 4 * TS_GROUPS;
+constexpr int TS_THREADS = (TS_PRODUCER_WARPS + 3) * 32;
+constexpr int TS_RAW_STAGES = 9;                                 // raw count tiles in flight (TMA runs this far ahead)
+constexpr int TS_B_STAGES = 4;
+constexpr int TS_RAW_BYTES = TC_TM * TC_TK * 2;                  // 16 KB raw uint16 tile
+constexpr int TS_PANEL_BYTES = 2 * TC_B_BYTES;                   // 16 KB [Q_hi | Q_lo]
+constexpr int TS_KC_BYTES = TC_TK * 4;                           // 256 B of per-k constants
+constexpr int TS_OFF_PANEL = TS_RAW_STAGES * TS_RAW_BYTES;
+constexpr int TS_OFF_KC = TS_OFF_PANEL + TS_B_STAGES * TS_PANEL_BYTES;
+constexpr int TS_OFF_BAR = TS_OFF_KC + TS_RAW_STAGES * TS_KC_BYTES;
+constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_GROUPS + 2 * TS_B_STAGES + 1;
+constexpr int TS_SMEM_BYTES = TS_OFF_BAR + 8 * TS_N_BARS + 16 + 1024 /*align*/;
+constexpr int TS_ACC_COLS = 192, TS_A_COLS = 64;   // D1 = [0, 128): A_hi [Q_hi | Q_lo];  D2 = [128, 192): A_lo Q_hi
+static_assert(TS_ACC_COLS + TS_GROUPS * TS_A_COLS <= TC_TMEM_COLS, "TMEM budget");
+static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared-memory budget");
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]; whole converged warp, one elected lane issues (see umma_bf16_w)
+template <bool ACCUM>
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACCUM ? 1 : 0) : "memory");
+}
+
+// 2-D tiled TMA load global -> shared, completion counted in bytes on an mbarrier; streaming data: evict-first in L2 so
+// that the panel tiles and constants (re-read by every CTA) stay resident
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int32_t x, int32_t y, uint32_t bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// residual of one entry: xf = the count as float, mu = r t
+template <bool LO_CLIP>
+__device__ __forceinline__ float resid1(float xf, float mu, float inv_theta, float clip) {
+    const float var = mu * fmaf(mu, inv_theta, 1.0f);
+    float v = (xf - mu) * rsqrt_approx(var);
+    v = fminf(v, clip);
+    if (LO_CLIP) v = fmaxf(v, -clip);
+    return v;
+}
+// two residuals -> one packed bf16 hi word (truncation) and one packed bf16 lo word (rounded remainder); the entry with
+// the lower k sits in the low half, which is the order the tensor core expects for a K-major 16-bit operand
+__device__ __forceinline__ void split_pair(float z0, float z1, uint32_t &h, uint32_t &l) {
+    const uint32_t b0 = __float_as_uint(z0), b1 = __float_as_uint(z1);
+    h = __byte_perm(b0, b1, 0x7632);
+    const float l0 = z0 - __uint_as_float(b0 & 0xffff0000u);
+    const float l1 = z1 - __uint_as_float(b1 & 0xffff0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(l0, l1);
+    l = *reinterpret_cast<const uint32_t *>(&lp);
+}
+
+template <int TRANS, bool LO_CLIP>
+__global__ void __launch_bounds__(TS_THREADS, 1)
+rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + TS_OFF_BAR;
+    const uint32_t bar_raw_full = bar_base, bar_raw_empty = bar_raw_full + 8 * TS_RAW_STAGES;
+    const uint32_t bar_a_full = bar_raw_empty + 8 * TS_RAW_STAGES, bar_a_empty = bar_a_full + 8 * TS_GROUPS;
+    const uint32_t bar_b_full = bar_a_empty + 8 * TS_GROUPS, bar_b_empty = bar_b_full + 8 * TS_B_STAGES;
+    const uint32_t bar_accum = bar_b_empty + 8 * TS_B_STAGES;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (bar_accum + 8 - smem_base));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_TM;
+    const int split = blockIdx.y;
+    const int64_t k_lo = split * a.k_per_split, k_hi = min(a.n_k, k_lo + a.k_per_split);
+    const int n_it = (int)ceil_div<int64_t>(max((int64_t)0, k_hi - k_lo), TC_TK);
+
+    if (warp == TS_PRODUCER_WARPS) {
+        if (lane == 0) {
+            for (int s = 0; s < TS_RAW_STAGES; ++s) {
+                mbar_init(bar_raw_full + 8 * s, 1);            // the copy issuer's arrive.expect_tx
+                mbar_init(bar_raw_empty + 8 * s, 4);           // one arrive per warp of the group that read the slot
+            }
+            for (int s = 0; s < TS_GROUPS; ++s) {
+                mbar_init(bar_a_full + 8 * s, 4);
+                mbar_init(bar_a_empty + 8 * s, 1);             // tcgen05.commit
+            }
+            for (int s = 0; s < TS_B_STAGES; ++s) {
+                mbar_init(bar_b_full + 8 * s, 1);
+                mbar_init(bar_b_empty + 8 * s, 1);
+            }
+            mbar_init(bar_accum, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32((const void *)tmem_slot), TC_TMEM_COLS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp < TS_PRODUCER_WARPS) {
+        // =============================== producers ===============================
+        const int group = warp >> 2, quarter = warp & 3;
+        const int m = quarter * 32 + lane;                                        // row of the tile = TMEM lane
+        // the constant of this thread's output row (TRANS 0: r of its cell, TRANS 1: s/T of its gene); the padded vectors
+        // hold 1.0 beyond the matrix, where TMA delivered zero counts: every residual stays finite
+        const float fixed = __ldg((TRANS == 0 ? a.rpad : a.tpad) + m0 + m);
+        const uint32_t a_col = tmem_d + ((uint32_t)(quarter * 32) << 16) + TS_ACC_COLS + (uint32_t)group * TS_A_COLS;
+        // TRANS 0: raw tile = 128 cells x 64 genes, 128-byte rows, TMA SWIZZLE_128B: 16-byte chunk c of row m sits at
+        //          chunk c ^ (m & 7) - eight consecutive lanes read eight different bank groups.
+        // TRANS 1: raw tile = 64 cells x 128 genes, 256-byte rows, no swizzle: a warp reads 32 consecutive uint16.
+        const uint32_t row_off = TRANS == 0 ? (uint32_t)m * 128u : (uint32_t)m * 2u;
+        const uint32_t swz = TRANS == 0 ? (uint32_t)(m & 7) : 0u;
+        uint32_t ph = 0;
+        for (int it = group; it < n_it; it += TS_GROUPS, ph ^= 1) {
+            const int rs = it % TS_RAW_STAGES;                    // raw slot of this stage (the TMA runs ahead of the groups)
+            const uint32_t raw_row = smem_base + rs * TS_RAW_BYTES + row_off;
+            const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
+            mbar_wait_backoff(bar_raw_full + 8 * rs, (uint32_t)(it / TS_RAW_STAGES) & 1);
+#pragma unroll
+            for (int c2 = 0; c2 < TC_TK / 16; ++c2) {             // 16 entries (k = 16 c2 .. 16 c2 + 15) per round
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c = 2 * c2 + half;                  // 16-byte chunk of 8 entries
+                    const uint4 k0 = lds128(kc_s + c * 32), k1 = lds128(kc_s + c * 32 + 16);   // warp-wide broadcast
+                    const float kc[8] = {__uint_as_float(k0.x), __uint_as_float(k0.y), __uint_as_float(k0.z),
+                                         __uint_as_float(k0.w), __uint_as_float(k1.x), __uint_as_float(k1.y),
+                                         __uint_as_float(k1.z), __uint_as_float(k1.w)};
+                    float z[8];
+                    if constexpr (TRANS == 0) {
+                        const uint4 raw = lds128(raw_row + (((uint32_t)c ^ swz) << 4));
+                        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            // exact uint16 -> float: splice the 16 bits under the 2^23 exponent, subtract 2^23
+                            const float x0 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7410)) - 8388608.0f;
+                            const float x1 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7432)) - 8388608.0f;
+                            z[2 * p] = resid1<LO_CLIP>(x0, fixed * kc[2 * p], a.inv_theta, a.clip);
+                            z[2 * p + 1] = resid1<LO_CLIP>(x1, fixed * kc[2 * p + 1], a.inv_theta, a.clip);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t v = lds_u16(raw_row + (uint32_t)(c * 8 + e) * 256u);
+                            const float xf = __uint_as_float(v | a.magic) - 8388608.0f;
+                            z[e] = resid1<LO_CLIP>(xf, fixed * kc[e], a.inv_theta, a.clip);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) split_pair(z[2 * p], z[2 * p + 1], hi[4 * half + p], lo[4 * half + p]);
+                }
+                if (c2 == 0) {
+                    // the TMEM slot was last read by the UMMAs of this group's previous stage
+                    mbar_wait_backoff(bar_a_empty + 8 * group, ph ^ 1);      // passes at once on the first lap
+                    tc_fence_after();
+                }
+                tmem_st8(a_col + 8 * c2, hi);                     // 16 bf16 = 8 columns
+                tmem_st8(a_col + 32 + 8 * c2, lo);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_raw_empty + 8 * rs);              // the raw slot may be refilled
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_full + 8 * group);
+        }
+
+        // =============================== epilogue ===============================
+        if (n_it > 0) {
+            mbar_wait(bar_accum, 0);
+            tc_fence_after();
+        }
+        if (warp < 16) {
+            // warp w reads TMEM lanes 32 (w % 4) .. +31 (= output rows), 16 output columns (w / 4) of both halves
+            const int col_q = warp >> 2;
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            if (n_it > 0) {
+                const uint32_t t0 = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col_q * 16);
+                // fixed summation order: hi.hi, hi.lo, lo.hi
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    uint32_t v[16];
+                    tmem_ld16(t0 + part * 64, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+                }
+            }
+            const int64_t row = m0 + m;
+            if (row < a.n_out) {
+                float4 *dst = reinterpret_cast<float4 *>(a.partials + ((int64_t)split * a.n_out + row) * TC_TN + col_q * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            }
+        }
+    } else if (warp == TS_PRODUCER_WARPS) {
+        // =============================== MMA issuer (whole warp, one elected lane issues) =============
+        constexpr uint32_t idesc128 = umma_idesc(0, 1, 128), idesc64 = umma_idesc(0, 1, 64);   // A K-major (TMEM), B MN-major
+        constexpr uint32_t b_lbo = 8192u, b_sbo = 1024u, b_kstep = 2048u;
+        const uint64_t db0 = umma_desc(smem_base + TS_OFF_PANEL, b_lbo, b_sbo);
+        const uint32_t b_hiw = (uint32_t)(db0 >> 32), b_low0 = (uint32_t)db0;
+        for (int it = 0; it < n_it; ++it) {
+            const int s = it % TS_GROUPS, sb = it % TS_B_STAGES;
+            mbar_wait(bar_b_full + 8 * sb, (uint32_t)(it / TS_B_STAGES) & 1);
+            mbar_wait(bar_a_full + 8 * s, (uint32_t)(it / TS_GROUPS) & 1);
+            tc_fence_after();
+            const uint32_t b_st = b_low0 + (uint32_t)sb * (TS_PANEL_BYTES >> 4);
+            const uint32_t a_st = tmem_d + TS_ACC_COLS + (uint32_t)s * TS_A_COLS;
+#pragma unroll
+            for (int k = 0; k < TC_TK / 16; ++k) {
+                const uint32_t bh = b_st + k * (b_kstep >> 4);
+                const uint32_t ah = a_st + 8 * k, al = a_st + 32 + 8 * k;        // K = 16 bf16 = 8 columns
+                if (it == 0 && k == 0) {
+                    umma_bf16_ts_w<false>(tmem_d, ah, bh, b_hiw, idesc128);
+                    umma_bf16_ts_w<false>(tmem_d + 128, al, bh, b_hiw, idesc64);
+                } else {
+                    umma_bf16_ts_w<true>(tmem_d, ah, bh, b_hiw, idesc128);
+                    umma_bf16_ts_w<true>(tmem_d + 128, al, bh, b_hiw, idesc64);
+                }
+            }
+            umma_commit_elect(bar_a_empty + 8 * s);           // frees the TMEM A slot when these MMAs have read it
+            umma_commit_elect(bar_b_empty + 8 * sb);          // ... and the panel stage
+        }
+        if (n_it > 0) umma_commit_elect(bar_accum);           // accumulator complete
+        __syncwarp();
+    } else if (warp == TS_PRODUCER_WARPS + 1) {
+        // =============================== raw-tile TMA issuer (one thread) ===============================
+        if (lane == 0) {
+            const uint64_t policy = l2_evict_first_policy();
+            const float *kconst = (TRANS == 0 ? a.tpad : a.rpad) + k_lo;
+            for (int it = 0; it < n_it; ++it) {
+                const int s = it % TS_RAW_STAGES;
+                const int32_t kk = (int32_t)(k_lo + (int64_t)it * TC_TK);
+                mbar_wait_backoff(bar_raw_empty + 8 * s, ((uint32_t)(it / TS_RAW_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(bar_raw_full + 8 * s, TS_RAW_BYTES + TS_KC_BYTES);
+                if (TRANS == 0) tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, kk, (int32_t)m0, bar_raw_full + 8 * s, policy);
+                else tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, (int32_t)m0, kk, bar_raw_full + 8 * s, policy);
+                bulk_g2s(smem_base + TS_OFF_KC + s * TS_KC_BYTES, kconst + (int64_t)it * TC_TK, TS_KC_BYTES, bar_raw_full + 8 * s);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== panel-tile copy issuer (one thread) ===============================
+        if (lane == 0) {
+            const char *qh = reinterpret_cast<const char *>(a.Qh) + (k_lo / TC_TK) * TC_B_BYTES;
+            const char *ql = reinterpret_cast<const char *>(a.Ql) + (k_lo / TC_TK) * TC_B_BYTES;
+            for (int it = 0; it < n_it; ++it) {
+                const int sb = it % TS_B_STAGES;
+                mbar_wait_backoff(bar_b_empty + 8 * sb, ((uint32_t)(it / TS_B_STAGES) & 1) ^ 1);
+                const uint32_t b_hi = smem_base + TS_OFF_PANEL + sb * TS_PANEL_BYTES;
+                mbar_arrive_expect_tx(bar_b_full + 8 * sb, TS_PANEL_BYTES);
+                bulk_g2s(b_hi, qh + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);
+                bulk_g2s(b_hi + TC_B_BYTES, ql + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TS_PRODUCER_WARPS) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+}
+
+// ---- host side: the tensor map of the count matrix -------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// counts: uint16 [C][ld]; box = (64 genes x 128 cells, SWIZZLE_128B) for M Q, (128 genes x 64 cells, no swizzle) for M^T Q
+static int make_counts_tensor_map(CUtensorMap *map, const uint16_t *counts, int64_t C, int64_t ld, int trans) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    GC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)C};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {trans == 0 ? (cuuint32_t)TC_TK : (cuuint32_t)TC_TM, trans == 0 ? (cuuint32_t)TC_TM : (cuuint32_t)TC_TK};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(counts), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, trans == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        char msg[96];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+        return fail("make_counts_tensor_map", msg);
+    }
+    return 0;
+}
+
+template <int TRANS, bool LO_CLIP>
+static int ts_launch(const CUtensorMap &map, const TcArgs &a, dim3 grid, cudaStream_t st) {
+    static thread_local bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev]) {
+        GC_CUDA(cudaFuncSetAttribute(rsvd_apply_ts_kernel<TRANS, LO_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TS_SMEM_BYTES));
+        configured[dev] = true;
+    }
+    rsvd_apply_ts_kernel<TRANS, LO_CLIP><<<grid, TS_THREADS, TS_SMEM_BYTES, st>>>(map, a);
+    return 0;
+}
+
+}  // namespace gc

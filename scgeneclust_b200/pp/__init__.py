@@ -1,1 +1,1 @@
-from ._preprocessing import normalize, reduce_dim
+from ._preprocessing import normalize, reduce_dim, start_omega

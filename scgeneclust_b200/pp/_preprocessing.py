@@ -10,7 +10,8 @@ import numpy as np
 import torch
 from loguru import logger
 
-from .._device import DeviceCounts, ResidualOperator, ingest_counts, randomized_pca
+from .._device import (DeviceCounts, ResidualOperator, ingest_counts, plan_pca, prefetch_omega,
+                       randomized_pca)
 
 STATE_KEY = "geneclust_b200"
 
@@ -24,6 +25,7 @@ class HotPathState:
     obsm_pca: Optional[torch.Tensor] = None
     redundancy: Optional[torch.Tensor] = None    # device copy of varp['redundancy']
     comm: object = None                          # optional GeneShardComm
+    omega: object = None                         # OmegaPrefetch started by `start_omega`
     info: dict = field(default_factory=dict)
 
 
@@ -33,6 +35,16 @@ def get_state(adata) -> HotPathState:
         st = HotPathState()
         adata.uns[STATE_KEY] = st
     return st
+
+
+def start_omega(adata, random_state: int = 0):
+    """Optional head start for `reduce_dim`: begin generating the randomized solver's test matrix (a sequential MT19937
+    stream, one CTA) on a side stream before the counts are uploaded / summed.  Purely an ordering optimisation: without
+    it `reduce_dim` generates the same matrix itself."""
+    from .._lib import require_cuda
+    require_cuda()
+    n_obs, n_vars = adata.shape
+    get_state(adata).omega = prefetch_omega(random_state, plan_pca(int(n_obs), int(n_vars), 'genes'), 'cuda')
 
 
 def normalize(adata, modality: Literal['sc', 'st'] = 'sc', materialize: bool = False):
@@ -66,7 +78,8 @@ def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):
     if st.op is None:
         raise RuntimeError("reduce_dim called before normalize")
     info = {}
-    st.varm_pca = randomized_pca(st.op, 'genes', random_state, info=info)
+    st.varm_pca = randomized_pca(st.op, 'genes', random_state, info=info, omega=st.omega)
+    st.omega = None
     st.info['gene_pca'] = info
     if st.comm is not None:
         st.varm_pca = st.comm.all_gather_rows(st.varm_pca)

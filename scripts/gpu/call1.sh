@@ -6,7 +6,7 @@ O=gpurun_out/r2c1
 mkdir -p $O
 nproc > $O/host.txt; free -g >> $O/host.txt; nvidia-smi -L >> $O/host.txt
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q -s > $O/pytest.log 2>&1; echo "pytest rc $?" >> $O/pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q -s > $O/pytest.log 2>&1; echo "pytest rc $?" >> $O/pytest.log
 # TS-mode draft: parity through the embed tests + timing
 python scripts/build_variant.py ts --replace scripts/experimental/rsvd_tc_ts.cu > $O/ts_build.log 2>&1
 GENECLUST_B200_LIB=$PWD/scripts/microbench/variants/libts.so timeout 300 python -m pytest tests/test_gpu_embed.py -m gpu -x -q > $O/ts_pytest.log 2>&1; echo "rc $?" >> $O/ts_pytest.log

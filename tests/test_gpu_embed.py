@@ -77,9 +77,11 @@ def test_count_sums_and_residuals(torch_cuda, small_counts):
         ResidualOperator.from_counts(ingest_counts(Xz))
 
 
-@pytest.mark.parametrize("simt", [True, False])
-def test_rsvd_passes_vs_numpy(torch_cuda, small_counts, simt):
-    """Y = M Q and Y = M^T Q over the implicit centred residual matrix against float64 numpy."""
+@pytest.mark.parametrize("kernel", ["ts", "ss", "simt"])
+def test_rsvd_passes_vs_numpy(torch_cuda, small_counts, kernel):
+    """Y = M Q and Y = M^T Q over the implicit centred residual matrix against float64 numpy, for the product kernel
+    (tcgen05, residual operand in tensor memory, TMA-fed count tiles) and the two cross-check kernels; ragged sizes
+    (1111 x ~1500: partial tiles in both directions, zero-filled by TMA / clamped loads)."""
     torch = torch_cuda
     from oracle import stages
     from scgeneclust_b200._device import ResidualOperator, ingest_counts
@@ -99,9 +101,9 @@ def test_rsvd_passes_vs_numpy(torch_cuda, small_counts, simt):
             M = Z - (rsft[:, None] if rsft is not None else 0) - (csft[None, :] if csft is not None else 0)
             ref = (M @ Q) if trans == 0 else (M.T @ Q)
             t = lambda a: None if a is None else torch.from_numpy(a.astype(np.float32)).cuda()  # noqa: E731
-            got = op.apply(trans, torch.from_numpy(Q).cuda(), t(rsft), t(csft), simt=simt).cpu().numpy()
+            got = op.apply(trans, torch.from_numpy(Q).cuda(), t(rsft), t(csft), kernel=kernel).cpu().numpy()
             scale = np.abs(ref).max()
-            assert np.abs(got[:, :60] - ref[:, :60]).max() <= 2e-4 * scale, (trans, simt)
+            assert np.abs(got[:, :60] - ref[:, :60]).max() <= 2e-4 * scale, (trans, kernel)
             assert not got[:, 60:].any()
 
 

@@ -64,10 +64,11 @@ def test_c3_pass_kernel_linearity_adjointness_and_simt_agreement(torch_cuda, c3_
     lhs = (W.double() * Y1.double()).sum()
     rhs = (Zt.double() * Q1.double()).sum()
     assert abs(float(lhs - rhs)) <= 1e-5 * max(abs(float(lhs)), float(W.double().norm() * Y1.double().norm()) * 1e-2)
-    Ys = op.apply(0, Q1, shift, None, simt=True)
-    assert float((Ys - Y1).abs().max()) <= 1e-4 * scale
-    Zs = op.apply(1, W, shift, None, simt=True)
-    assert float((Zs - Zt).abs().max()) <= 1e-4 * float(Zt.abs().max())
+    for kernel in ("simt", "ss"):
+        Ys = op.apply(0, Q1, shift, None, kernel=kernel)
+        assert float((Ys - Y1).abs().max()) <= 1e-4 * scale, kernel
+        Zs = op.apply(1, W, shift, None, kernel=kernel)
+        assert float((Zs - Zt).abs().max()) <= 1e-4 * float(Zt.abs().max()), kernel
     # determinism: the split-K reduction order is fixed
     assert torch.equal(op.apply(0, Q1, shift, None), Y1)
 
