@@ -234,6 +234,15 @@ int gc_mi_cd(const double *XR, int64_t ldr, int64_t G, int n, const int32_t *lab
  * (N - 1 iff the graph is connected).  scratch: gc_mst_scratch_bytes(N), 256-byte aligned.  No host synchronisation. */
 int64_t gc_mst_scratch_bytes(int64_t N);
 int gc_mst_boruvka(const double *R, int64_t N, int32_t *edges_out, int32_t *n_edges_out, void *scratch, void *stream);
+/* The same forest from edge lists, so that the N x N matrix never has to exist: the edges are the condensed pair range
+ * [p_begin, p_begin + n_cond) (itertools.combinations order, values cond[0..n_cond)) plus n_extra explicit edges
+ * (extra_u, extra_v, extra_w) - the forest carried over from earlier tiles or gathered from other ranks.  Non-positive
+ * weights are non-edges.  Same strict edge order as gc_mst_boruvka (larger MI, then smaller condensed index), hence the
+ * same forest: MSF(E1 u E2) = MSF(MSF(E1) u E2).  Outputs up to N - 1 edges (u < v) with their weights; *n_out = count.
+ * The output arrays must not alias the explicit input edges.  scratch: gc_mst_scratch_bytes(N). */
+int gc_mst_boruvka_edges(const double *cond, int64_t p_begin, int64_t n_cond, const int32_t *extra_u,
+                         const int32_t *extra_v, const double *extra_w, int64_t n_extra, int64_t N, int32_t *out_u,
+                         int32_t *out_v, double *out_w, int32_t *n_out, void *scratch, void *stream);
 
 /* HOST function (all pointers are host memory, no GPU work): the HDBSCAN tail of GeneClust-ps
  * (scGeneClust/tl/cluster.py:127-130: hdbscan label -> condense_tree(., min_cluster_size) -> compute_stability ->

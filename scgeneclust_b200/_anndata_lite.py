@@ -80,12 +80,78 @@ class DeviceMatrix:
         return DeviceMatrix(self.tensor.index_select(axis, idx[axis]).contiguous())
 
 
+class ShardedMatrix:
+    """Gene-sharded stand-in for `adata.X` in a multi-rank GeneClust-ps run: this rank holds the residual columns of ITS
+    genes (`tensor`: cells x local genes, device), the AnnData describes the global matrix.  `positions` are the indices
+    of the local columns in the CURRENT global column order (ranks own ascending, disjoint index sets, so concatenating
+    the shards in rank order gives the global order).  Row subsets apply to every shard alike; a column subset given in
+    global indices keeps the local columns it names."""
+    ndim = 2
+
+    def __init__(self, tensor, positions: np.ndarray, n_cols_total: int, comm):
+        self.tensor, self.positions, self.n_cols_total, self.comm = tensor, np.asarray(positions, dtype=np.int64), int(n_cols_total), comm
+
+    @property
+    def shape(self):
+        return (int(self.tensor.shape[0]), self.n_cols_total)
+
+    @property
+    def dtype(self):
+        return np.dtype(str(self.tensor.dtype).replace("torch.", ""))
+
+    def copy(self):
+        return ShardedMatrix(self.tensor.clone(), self.positions.copy(), self.n_cols_total, self.comm)
+
+    def __array__(self, dtype=None, copy=None):
+        raise TypeError("a gene-sharded matrix has no single host copy; use gather_columns() on the ranks")
+
+    def __getitem__(self, key):
+        import torch
+        if not (isinstance(key, tuple) and len(key) == 2):
+            raise IndexError("ShardedMatrix supports x[rows, :] and x[:, cols] only")
+        rows, cols = key
+        t, positions, total = self.tensor, self.positions, self.n_cols_total
+        if not (isinstance(rows, slice) and rows == slice(None)):
+            r = np.asarray(rows)
+            r = np.flatnonzero(r) if r.dtype == bool else r.astype(np.int64)
+            t = t.index_select(0, torch.from_numpy(r).to(t.device))
+        if not (isinstance(cols, slice) and cols == slice(None)):
+            c = np.asarray(cols)
+            c = np.flatnonzero(c) if c.dtype == bool else c.astype(np.int64)
+            if np.any(np.diff(c) <= 0):
+                raise IndexError("ShardedMatrix column subsets must be strictly increasing global indices")
+            new_pos = np.searchsorted(c, positions)                  # where each local column lands in the new order
+            new_pos_c = np.minimum(new_pos, len(c) - 1) if len(c) else new_pos
+            keep = (new_pos < len(c)) & (c[new_pos_c] == positions) if len(c) else np.zeros(len(positions), bool)
+            t = t.index_select(1, torch.from_numpy(np.flatnonzero(keep)).to(t.device))
+            positions, total = new_pos[keep], len(c)
+        return ShardedMatrix(t.contiguous(), positions, total, self.comm)
+
+    def gather_columns(self):
+        """The full (cells x all current columns) matrix on every rank (all-gather over the gene shards)."""
+        import torch
+        import torch.distributed as dist
+        comm = self.comm
+        n_rows = int(self.tensor.shape[0])
+        counts = [torch.zeros(1, dtype=torch.int64, device=self.tensor.device) for _ in range(comm.world)]
+        dist.all_gather(counts, torch.tensor([self.tensor.shape[1]], dtype=torch.int64, device=self.tensor.device), group=comm.group)
+        counts = [int(c.item()) for c in counts]
+        width = max(max(counts), 1)
+        pad = torch.zeros((width, n_rows), dtype=self.tensor.dtype, device=self.tensor.device)   # columns as rows: contiguous
+        pad[:self.tensor.shape[1]] = self.tensor.t()
+        parts = [torch.empty_like(pad) for _ in range(comm.world)]
+        dist.all_gather(parts, pad, group=comm.group)
+        full = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0).t().contiguous()
+        assert full.shape[1] == self.n_cols_total
+        return full
+
+
 class AnnDataLite:
     """`n_obs` x `n_vars` annotated matrix: `.X`, `.obs`, `.var`, `.obsm`, `.varm`, `.obsp`, `.varp`, `.uns`."""
 
     def __init__(self, X, obs: Optional[pd.DataFrame] = None, var: Optional[pd.DataFrame] = None,
                  obs_names=None, var_names=None):
-        if not (issparse(X) or isinstance(X, (np.ndarray, DeviceMatrix)) or getattr(X, "is_device_counts", False)):
+        if not (issparse(X) or isinstance(X, (np.ndarray, DeviceMatrix, ShardedMatrix)) or getattr(X, "is_device_counts", False)):
             X = np.asarray(X)
         if X.ndim != 2:
             raise ValueError(f"X must be 2-D, got shape {X.shape}")

@@ -501,55 +501,96 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         Qp = Qp[comm.gene_lo:comm.gene_hi].contiguous()
 
     alg = PanelAlgebra(dev, max(op.C, op.G))
-    buf_c = torch.empty((op.C, Q_LD), dtype=torch.float32, device=dev)
+    # Gene-sharded input: a cell-space panel (cells x 64) is the SUM over the gene shards of every rank's partial product.
+    # It is never all-reduced and normalised redundantly: reduce-scatter hands every rank one row chunk of the sum, the
+    # Cholesky-QR runs on that chunk (64 x 64 Gram all-reduced), and the normalised chunks are all-gathered - the same
+    # NVLink bytes as the all-reduce, 1/world of the panel algebra per rank.
+    sliced = comm is not None and comm.world > 1
+    if sliced:
+        chunk = comm.row_chunk(op.C)
+        c_pad = chunk * comm.world
+        valid = max(0, min(chunk, op.C - comm.rank * chunk))           # real rows of this rank's chunk
+        tmp_c_pad = torch.zeros((c_pad, Q_LD), dtype=torch.float32, device=dev)
+        buf_c_pad = torch.zeros((c_pad, Q_LD), dtype=torch.float32, device=dev)
+        tmp_c, buf_c = tmp_c_pad[:op.C], buf_c_pad[:op.C]
+        sl_in = torch.zeros((chunk, Q_LD), dtype=torch.float32, device=dev)
+        sl_a, sl_b = torch.zeros_like(sl_in), torch.zeros_like(sl_in)
+    else:
+        buf_c = torch.empty((op.C, Q_LD), dtype=torch.float32, device=dev)
+        tmp_c = torch.empty_like(buf_c)
     buf_g = torch.empty((op.G, Q_LD), dtype=torch.float32, device=dev)
-    tmp_c, tmp_g = torch.empty_like(buf_c), torch.empty_like(buf_g)
+    tmp_g = torch.empty_like(buf_g)
 
     def apply(trans, Qin):
+        """Raw pass.  Gene-sharded trans = 0 output is this rank's PARTIAL sum (in tmp_c): `normalise` reduces it."""
         out = tmp_c if trans == 0 else tmp_g
         op.apply(trans, Qin, row_shift, col_shift, out=out, simt=simt)
-        if comm is not None and trans == 0:
-            comm.all_reduce_sum(out)       # cell-space panel = sum over gene shards
         return out
 
-    def normalise(trans, Y):
-        # rows of Y: cells (replicated across shards) for trans=0, local genes for trans=1
-        dst = buf_c if trans == 0 else buf_g
-        # trans == 1: rows = this rank's genes (sharded); trans == 0: rows = all cells, replicated after the all-reduce
-        return alg.chol_qr(Y, q, dst, comm, replicated=(trans == 0))
+    def chol_qr_chunk(cur, n_steps=1):
+        """Cholesky-QR of the row-sliced panel whose chunk on this rank is `cur` (chunk x 64, zero pad rows); returns the
+        normalised FULL panel (all-gathered into buf_c)."""
+        for _ in range(n_steps):
+            nxt = sl_a if cur is not sl_a else sl_b
+            if valid > 0:
+                alg.chol_qr(cur[:valid], q, nxt[:valid], comm, replicated=False)
+            else:                                    # a rank past the end of the panel still joins the Gram all-reduce
+                alg.gram.zero_()
+                comm.all_reduce_sum(alg.gram)
+            cur = nxt
+        comm.all_gather_chunks(cur, buf_c_pad)
+        return buf_c
+
+    def normalise(trans, Y, n_steps=1):
+        """Orthonormalise the columns of the panel Y (Cholesky-QR, `n_steps` rounds).  trans == 1: rows = this rank's genes
+        (sharded, local Gram all-reduced); trans == 0: rows = all cells."""
+        if trans == 0 and sliced:
+            comm.reduce_scatter_rows(tmp_c_pad, sl_in)         # Y is tmp_c: this rank's partial sums
+            return chol_qr_chunk(sl_in, n_steps)
+        cur, dst = Y, (buf_c if trans == 0 else buf_g)
+        for step in range(n_steps):
+            out = dst if step % 2 == 0 else Y                  # ping-pong: the second round writes back into Y's buffer
+            alg.chol_qr(cur, q, out, comm if trans == 1 else None, replicated=False)
+            cur = out
+        return cur
 
     Qcur = Qp
     for it in range(n_iter):
         if it == 0 and ones_trick:
-            # raw first pass with the ones column; row n_out of `ext` carries the column sums of Omega so that one
-            # all-reduce (gene-sharded, trans 0) covers both
-            n_out = op.C if fwd == 0 else op.G
+            # raw first pass with a column of ones in Omega's last padding slot: column 63 of the product is Z 1
             n_k_total = G_total if fwd == 0 else op.C
-            ext = torch.empty((n_out + 1, Q_LD), dtype=torch.float32, device=dev)
             Qp[:, Q_LD - 1] = 1.0
-            op.apply(fwd, Qp, None, None, out=ext[:n_out], simt=simt)
-            ext[n_out] = Qp.sum(dim=0, dtype=torch.float64).to(torch.float32)
-            if comm is not None and fwd == 0:
-                comm.all_reduce_sum(ext)
-            shift = (ext[:n_out, Q_LD - 1] / float(n_k_total)).contiguous()
-            Y = tmp_c if fwd == 0 else tmp_g
-            torch.addcmul(ext[:n_out], shift.unsqueeze(1), ext[n_out].unsqueeze(0), value=-1.0, out=Y)
-            Y[:, q:] = 0.0
+            Y = apply(fwd, Qp)
+            colsum = Qp.sum(dim=0, dtype=torch.float64).to(torch.float32)
+            if sliced and fwd == 0:
+                comm.all_reduce_sum(colsum)                    # Omega's rows are sharded like the genes
+                comm.reduce_scatter_rows(tmp_c_pad, sl_in)
+                part = sl_in                                   # this rank's chunk of the summed raw product
+            else:
+                part = Y
+            shift = (part[:, Q_LD - 1] / float(n_k_total)).contiguous()
+            torch.addcmul(part, shift.unsqueeze(1), colsum.unsqueeze(0), value=-1.0, out=part)
+            part[:, q:] = 0.0
+            if sliced and fwd == 0:
+                shift_full = torch.empty(c_pad, dtype=torch.float32, device=dev)
+                comm.all_gather_chunks(shift, shift_full)
+                shift = shift_full[:op.C].contiguous()
+                Qcur = chol_qr_chunk(part)
+            else:
+                Qcur = normalise(fwd, part)
             if samples == "genes":
                 row_shift = shift
             else:
                 col_shift = shift
-            Qcur = normalise(fwd, Y)
         else:
             Qcur = normalise(fwd, apply(fwd, Qcur))
         Qcur = normalise(bwd, apply(bwd, Qcur))
     # final range: orthonormal basis by two Cholesky-QR steps (qr_normalizer of extmath.py:386)
-    Y = apply(fwd, Qcur)
-    Q1 = alg.chol_qr(Y, q, buf_c if fwd == 0 else buf_g, comm, replicated=(fwd == 0))
-    Qf = alg.chol_qr(Q1, q, Y, comm, replicated=(fwd == 0))      # second pass writes into the tmp buffer
-    Qf = Qf.clone()
+    Qf = normalise(fwd, apply(fwd, Qcur), n_steps=2).clone()
     Bt = apply(bwd, Qf)                                  # B^T = A^T Q  (A.shape[1] x q)
     # thin SVD of B through the q x q eigenproblem  B B^T = Uhat S^2 Uhat^T  (float64, on the device)
+    if sliced and bwd == 0:
+        comm.all_reduce_sum(Bt)                          # cell-space B^T (sklearn did not transpose): needed in full
     alg.gram_of(Bt, comm, replicated=(bwd == 0))
     evals = torch.empty(Q_LD, dtype=torch.float64, device=dev)
     uhat = torch.empty((Q_LD, Q_LD), dtype=torch.float32, device=dev)

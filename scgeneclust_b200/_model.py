@@ -68,6 +68,9 @@ def scGeneClust(
     # head start for the gene PCA: its Omega test matrix is a sequential MT19937 stream (one CTA), so it is started on a
     # side stream before the counts are uploaded and summed
     pp.start_omega(copied_adata, random_state)
+    # varp['redundancy'] (N x N) is part of the out-contract only with return_info: otherwise GeneClust-ps streams the
+    # MI tiles into the spanning forest and never builds the matrix
+    pp.get_state(copied_adata).dense_redundancy = bool(return_info)
     # preprocessing: residuals stay an implicit device operator for `fast`; `ps` and `return_info` need them dense
     pp.normalize(copied_adata, modality, materialize=(version == 'ps' or return_info))
     pp.reduce_dim(copied_adata, version, random_state)
@@ -90,6 +93,9 @@ def scGeneClust(
         # the device-side state (counts, residuals, PCA buffers, N x N redundancy) is not part of the reference's
         # out-contract, cannot be pickled / written to h5ad and would pin gigabytes of HBM for the life of the result
         copied_adata.uns.pop(STATE_KEY, None)
+        from ._anndata_lite import ShardedMatrix
+        if isinstance(copied_adata.X, ShardedMatrix):         # gene-sharded run: gather the residual columns (collective)
+            copied_adata._X = copied_adata.X.gather_columns().cpu().numpy()
         if isinstance(copied_adata.X, DeviceMatrix):          # hand the residuals back as the ndarray the reference returns
             copied_adata.X = np.asarray(copied_adata.X)
         for slot in (copied_adata.varp, copied_adata.varm, copied_adata.obsm):

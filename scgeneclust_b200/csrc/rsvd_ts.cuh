@@ -31,7 +31,14 @@
 
 namespace gc {
 
-constexpr int TS_GROUPS = 5;
+#ifndef TS_GROUPS_N          // developer knobs (scripts/build_variant.py -DTS_GROUPS_N=.. -DTS_A_STAGES_N=..)
+#define TS_GROUPS_N 4
+#endif
+#ifndef TS_A_STAGES_N
+#define TS_A_STAGES_N 5
+#endif
+constexpr int TS_GROUPS = TS_GROUPS_N;                           // producer groups of four warps
+constexpr int TS_A_STAGES = TS_A_STAGES_N;                       // A-operand slots in tensor memory (64 columns each)
 constexpr int TS_PRODUCER_WARPS = 4 * TS_GROUPS;
 constexpr int TS_THREADS = (TS_PRODUCER_WARPS + 3) * 32;
 constexpr int TS_RAW_STAGES = 9;                                 // raw count tiles in flight (TMA runs this far ahead)
@@ -42,10 +49,11 @@ constexpr int TS_KC_BYTES = TC_TK * 4;                           // 256 B of per
 constexpr int TS_OFF_PANEL = TS_RAW_STAGES * TS_RAW_BYTES;
 constexpr int TS_OFF_KC = TS_OFF_PANEL + TS_B_STAGES * TS_PANEL_BYTES;
 constexpr int TS_OFF_BAR = TS_OFF_KC + TS_RAW_STAGES * TS_KC_BYTES;
-constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_GROUPS + 2 * TS_B_STAGES + 1;
+constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * TS_B_STAGES + 1;
 constexpr int TS_SMEM_BYTES = TS_OFF_BAR + 8 * TS_N_BARS + 16 + 1024 /*align*/;
 constexpr int TS_ACC_COLS = 192, TS_A_COLS = 64;   // D1 = [0, 128): A_hi [Q_hi | Q_lo];  D2 = [128, 192): A_lo Q_hi
-static_assert(TS_ACC_COLS + TS_GROUPS * TS_A_COLS <= TC_TMEM_COLS, "TMEM budget");
+static_assert(TS_ACC_COLS + TS_A_STAGES * TS_A_COLS <= TC_TMEM_COLS, "TMEM budget");
+static_assert(TS_GROUPS >= 4, "the epilogue uses sixteen producer warps");
 static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared-memory budget");
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -65,6 +73,54 @@ __device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a,
         "setp.ne.b32 p, %5, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACCUM ? 1 : 0) : "memory");
+}
+
+// All UMMAs of one 128 x 64 stage (four k slices x {A_hi [Q_hi | Q_lo] -> D1, A_lo Q_hi -> D2}) and the two commits that
+// release the stage's TMEM slot and panel tile, issued by ONE elected lane from ONE asm block.  The MMA-issuing warp is a
+// serial resource: it shares its scheduler with four producer warps that are always ready to issue, so every instruction
+// in its loop costs ~5 issue cycles.  Issuing each UMMA from its own wrapper (elect + predicate vote + four vector ->
+// uniform register moves each) made that loop ~200 instructions per stage, i.e. as long as the stage itself, and the
+// producers waited for TMEM slots (25-32 % of all stall samples); here it is one elect and straight-line UMMAs.
+//   d: accumulator base (D1 = d, D2 = d + 128); a: the stage's A slot (hi at +0, lo at +32 columns; K = 16 is 8 columns);
+//   b_lo / b_hi: shared-memory descriptor of the panel tile (K step = 2048 B >> 4 = 128); first != 0 accumulates slice 0.
+__device__ __forceinline__ void umma_stage_ts(uint32_t d, uint32_t a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc128,
+                                              uint32_t idesc64, uint32_t accumulate_first, uint32_t bar_a, uint32_t bar_b) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p1, q;\n\t"
+        ".reg .b32 d2, a1, a2, a3, l0, l1, l2, l3, b1, b2, b3;\n\t"
+        ".reg .b64 db0, db1, db2, db3;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p0, %6, 0;\n\t"
+        "setp.eq.b32 p1, 0, 0;\n\t"
+        "add.u32 d2, %0, 128;\n\t"
+        "add.u32 a1, %1, 8;\n\t"
+        "add.u32 a2, %1, 16;\n\t"
+        "add.u32 a3, %1, 24;\n\t"
+        "add.u32 l0, %1, 32;\n\t"
+        "add.u32 l1, %1, 40;\n\t"
+        "add.u32 l2, %1, 48;\n\t"
+        "add.u32 l3, %1, 56;\n\t"
+        "add.u32 b1, %2, 128;\n\t"
+        "add.u32 b2, %2, 256;\n\t"
+        "add.u32 b3, %2, 384;\n\t"
+        "mov.b64 db0, {%2, %3};\n\t"
+        "mov.b64 db1, {b1, %3};\n\t"
+        "mov.b64 db2, {b2, %3};\n\t"
+        "mov.b64 db3, {b3, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db0, %4, p0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d2], [l0], db0, %5, p0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], db1, %4, p1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d2], [l1], db1, %5, p1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], db2, %4, p1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d2], [l2], db2, %5, p1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], db3, %4, p1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [d2], [l3], db3, %5, p1;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "}"
+        ::"r"(d), "r"(a), "r"(b_lo), "r"(b_hi), "r"(idesc128), "r"(idesc64), "r"(accumulate_first), "r"(bar_a), "r"(bar_b)
+        : "memory");
 }
 
 // 2-D tiled TMA load global -> shared, completion counted in bytes on an mbarrier; streaming data: evict-first in L2 so
@@ -119,8 +175,8 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + TS_OFF_BAR;
     const uint32_t bar_raw_full = bar_base, bar_raw_empty = bar_raw_full + 8 * TS_RAW_STAGES;
-    const uint32_t bar_a_full = bar_raw_empty + 8 * TS_RAW_STAGES, bar_a_empty = bar_a_full + 8 * TS_GROUPS;
-    const uint32_t bar_b_full = bar_a_empty + 8 * TS_GROUPS, bar_b_empty = bar_b_full + 8 * TS_B_STAGES;
+    const uint32_t bar_a_full = bar_raw_empty + 8 * TS_RAW_STAGES, bar_a_empty = bar_a_full + 8 * TS_A_STAGES;
+    const uint32_t bar_b_full = bar_a_empty + 8 * TS_A_STAGES, bar_b_empty = bar_b_full + 8 * TS_B_STAGES;
     const uint32_t bar_accum = bar_b_empty + 8 * TS_B_STAGES;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (bar_accum + 8 - smem_base));
@@ -137,7 +193,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 mbar_init(bar_raw_full + 8 * s, 1);            // the copy issuer's arrive.expect_tx
                 mbar_init(bar_raw_empty + 8 * s, 4);           // one arrive per warp of the group that read the slot
             }
-            for (int s = 0; s < TS_GROUPS; ++s) {
+            for (int s = 0; s < TS_A_STAGES; ++s) {
                 mbar_init(bar_a_full + 8 * s, 4);
                 mbar_init(bar_a_empty + 8 * s, 1);             // tcgen05.commit
             }
@@ -163,15 +219,19 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         // the constant of this thread's output row (TRANS 0: r of its cell, TRANS 1: s/T of its gene); the padded vectors
         // hold 1.0 beyond the matrix, where TMA delivered zero counts: every residual stays finite
         const float fixed = __ldg((TRANS == 0 ? a.rpad : a.tpad) + m0 + m);
-        const uint32_t a_col = tmem_d + ((uint32_t)(quarter * 32) << 16) + TS_ACC_COLS + (uint32_t)group * TS_A_COLS;
+        const uint32_t a_lane = tmem_d + ((uint32_t)(quarter * 32) << 16) + TS_ACC_COLS;
         // TRANS 0: raw tile = 128 cells x 64 genes, 128-byte rows, TMA SWIZZLE_128B: 16-byte chunk c of row m sits at
         //          chunk c ^ (m & 7) - eight consecutive lanes read eight different bank groups.
         // TRANS 1: raw tile = 64 cells x 128 genes, 256-byte rows, no swizzle: a warp reads 32 consecutive uint16.
         const uint32_t row_off = TRANS == 0 ? (uint32_t)m * 128u : (uint32_t)m * 2u;
         const uint32_t swz = TRANS == 0 ? (uint32_t)(m & 7) : 0u;
-        uint32_t ph = 0;
-        for (int it = group; it < n_it; it += TS_GROUPS, ph ^= 1) {
+        for (int it = group; it < n_it; it += TS_GROUPS) {
             const int rs = it % TS_RAW_STAGES;                    // raw slot of this stage (the TMA runs ahead of the groups)
+            // TMEM A slot of this stage.  There are more slots than groups: the slot was last used by stage it - TS_A_STAGES,
+            // an EARLIER stage than this group's previous one, so its UMMAs have normally retired by now (with one slot per
+            // group every group waited for its own, most recently issued, UMMAs: 32 % of all stall samples)
+            const int as = it % TS_A_STAGES;
+            const uint32_t a_col = a_lane + (uint32_t)as * TS_A_COLS;
             const uint32_t raw_row = smem_base + rs * TS_RAW_BYTES + row_off;
             const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
             mbar_wait_backoff(bar_raw_full + 8 * rs, (uint32_t)(it / TS_RAW_STAGES) & 1);
@@ -210,7 +270,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 }
                 if (c2 == 0) {
                     // the TMEM slot was last read by the UMMAs of this group's previous stage
-                    mbar_wait_backoff(bar_a_empty + 8 * group, ph ^ 1);      // passes at once on the first lap
+                    mbar_wait_backoff(bar_a_empty + 8 * as, ((uint32_t)(it / TS_A_STAGES) & 1) ^ 1);   // passes at once on the first lap
                     tc_fence_after();
                 }
                 tmem_st8(a_col + 8 * c2, hi);                     // 16 bf16 = 8 columns
@@ -221,7 +281,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a_full + 8 * group);
+            if (lane == 0) mbar_arrive(bar_a_full + 8 * as);
         }
 
         // =============================== epilogue ===============================
@@ -229,7 +289,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             mbar_wait(bar_accum, 0);
             tc_fence_after();
         }
-        if (warp < 16) {
+        if (warp < 16 && warp < TS_PRODUCER_WARPS) {
             // warp w reads TMEM lanes 32 (w % 4) .. +31 (= output rows), 16 output columns (w / 4) of both halves
             const int col_q = warp >> 2;
             float acc[16];
@@ -257,30 +317,20 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     } else if (warp == TS_PRODUCER_WARPS) {
         // =============================== MMA issuer (whole warp, one elected lane issues) =============
         constexpr uint32_t idesc128 = umma_idesc(0, 1, 128), idesc64 = umma_idesc(0, 1, 64);   // A K-major (TMEM), B MN-major
-        constexpr uint32_t b_lbo = 8192u, b_sbo = 1024u, b_kstep = 2048u;
+        constexpr uint32_t b_lbo = 8192u, b_sbo = 1024u;          // K step 2048 B: see umma_stage_ts
         const uint64_t db0 = umma_desc(smem_base + TS_OFF_PANEL, b_lbo, b_sbo);
         const uint32_t b_hiw = (uint32_t)(db0 >> 32), b_low0 = (uint32_t)db0;
+        // warp-uniform copy of the TMEM base (it came out of shared memory through a vector load): everything derived from
+        // it can then live in uniform registers
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
         for (int it = 0; it < n_it; ++it) {
-            const int s = it % TS_GROUPS, sb = it % TS_B_STAGES;
+            const int s = it % TS_A_STAGES, sb = it % TS_B_STAGES;
             mbar_wait(bar_b_full + 8 * sb, (uint32_t)(it / TS_B_STAGES) & 1);
-            mbar_wait(bar_a_full + 8 * s, (uint32_t)(it / TS_GROUPS) & 1);
+            mbar_wait(bar_a_full + 8 * s, (uint32_t)(it / TS_A_STAGES) & 1);
             tc_fence_after();
-            const uint32_t b_st = b_low0 + (uint32_t)sb * (TS_PANEL_BYTES >> 4);
-            const uint32_t a_st = tmem_d + TS_ACC_COLS + (uint32_t)s * TS_A_COLS;
-#pragma unroll
-            for (int k = 0; k < TC_TK / 16; ++k) {
-                const uint32_t bh = b_st + k * (b_kstep >> 4);
-                const uint32_t ah = a_st + 8 * k, al = a_st + 32 + 8 * k;        // K = 16 bf16 = 8 columns
-                if (it == 0 && k == 0) {
-                    umma_bf16_ts_w<false>(tmem_d, ah, bh, b_hiw, idesc128);
-                    umma_bf16_ts_w<false>(tmem_d + 128, al, bh, b_hiw, idesc64);
-                } else {
-                    umma_bf16_ts_w<true>(tmem_d, ah, bh, b_hiw, idesc128);
-                    umma_bf16_ts_w<true>(tmem_d + 128, al, bh, b_hiw, idesc64);
-                }
-            }
-            umma_commit_elect(bar_a_empty + 8 * s);           // frees the TMEM A slot when these MMAs have read it
-            umma_commit_elect(bar_b_empty + 8 * sb);          // ... and the panel stage
+            umma_stage_ts(tmem_u, tmem_u + TS_ACC_COLS + (uint32_t)s * TS_A_COLS,
+                          b_low0 + (uint32_t)sb * (TS_PANEL_BYTES >> 4), b_hiw, idesc128, idesc64, it > 0 ? 1u : 0u,
+                          bar_a_empty + 8 * s, bar_b_empty + 8 * sb);
         }
         if (n_it > 0) umma_commit_elect(bar_accum);           // accumulator complete
         __syncwarp();

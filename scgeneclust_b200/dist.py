@@ -83,6 +83,31 @@ class GeneShardComm:
         dist.all_gather(parts, pad, group=self.group)
         return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, self.bounds)], dim=0).contiguous()
 
+    # -- row-sliced panels (cells x 64 panels that are sums over gene shards) ------------------------------
+    def row_chunk(self, n_rows: int) -> int:
+        """Rows per rank when an n_rows panel is cut into `world` equal chunks (the last ones zero padded)."""
+        return -(-n_rows // self.world)
+
+    def reduce_scatter_rows(self, full_padded: torch.Tensor, out_chunk: torch.Tensor) -> torch.Tensor:
+        """out_chunk = this rank's row chunk of the SUM over ranks of `full_padded` (world * chunk rows)."""
+        if self.world == 1:
+            out_chunk.copy_(full_padded)
+        elif dist.get_backend(self.group) == "gloo":          # gloo has no reduce-scatter: CPU-test / one-GPU path
+            dist.all_reduce(full_padded, op=dist.ReduceOp.SUM, group=self.group)
+            c = out_chunk.shape[0]
+            out_chunk.copy_(full_padded[self.rank * c:(self.rank + 1) * c])
+        else:
+            dist.reduce_scatter_tensor(out_chunk, full_padded, op=dist.ReduceOp.SUM, group=self.group)
+        return out_chunk
+
+    def all_gather_chunks(self, chunk: torch.Tensor, out_full: torch.Tensor) -> torch.Tensor:
+        """out_full (world * chunk rows) = the per-rank chunks in rank order."""
+        if self.world == 1:
+            out_full.copy_(chunk)
+        else:
+            dist.all_gather_into_tensor(out_full, chunk.contiguous(), group=self.group)
+        return out_full
+
     def split_range(self, n: int) -> Tuple[int, int]:
         """This rank's contiguous slice of range(n) (e.g. of the condensed gene-pair index space)."""
         per = -(-n // self.world)

@@ -24,6 +24,8 @@ class HotPathState:
     varm_pca: Optional[torch.Tensor] = None      # device copy of varm['X_pca']
     obsm_pca: Optional[torch.Tensor] = None
     redundancy: Optional[torch.Tensor] = None    # device copy of varp['redundancy']
+    dense_redundancy: bool = True                # False: the entry point does not return varp['redundancy'] -> stream it
+    forest: Optional[tuple] = None               # (edges (n, 2) int64, redundancy of each edge) from the streamed stage
     comm: object = None                          # optional GeneShardComm
     omega: object = None                         # OmegaPrefetch started by `start_omega`
     info: dict = field(default_factory=dict)
@@ -63,12 +65,15 @@ def normalize(adata, modality: Literal['sc', 'st'] = 'sc', materialize: bool = F
     st.op = ResidualOperator.from_counts(counts)
     adata.uns['pearson_residuals_normalization'] = {'theta': st.op.theta, 'clip': None, 'computed_on': 'adata.X'}
     if materialize:
+        st.Z = st.op.materialize()                   # gene-sharded input: the residual columns of this rank's genes
+        from .._anndata_lite import AnnDataLite, DeviceMatrix, ShardedMatrix
         if st.comm is not None:
-            raise NotImplementedError("dense residuals (GeneClust-ps / return_info) need the unsharded matrix")
-        st.Z = st.op.materialize()
-        from .._anndata_lite import AnnDataLite, DeviceMatrix
-        # AnnDataLite carries the device matrix itself (downloaded on first host use); a real AnnData needs an ndarray
-        adata.X = DeviceMatrix(st.Z) if isinstance(adata, AnnDataLite) else st.Z.cpu().numpy()
+            if not isinstance(adata, AnnDataLite):
+                raise NotImplementedError("gene-sharded dense residuals need the AnnDataLite container")
+            adata.X = ShardedMatrix(st.Z, np.arange(st.comm.gene_lo, st.comm.gene_hi), st.comm.total_genes, st.comm)
+        else:
+            # AnnDataLite carries the device matrix itself (downloaded on first host use); a real AnnData needs an ndarray
+            adata.X = DeviceMatrix(st.Z) if isinstance(adata, AnnDataLite) else st.Z.cpu().numpy()
 
 
 def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):

@@ -26,9 +26,9 @@ def find_high_confidence_cells(adata, n_obs_clusters: int, n_components: int = 1
         keep = np.ones(adata.n_obs, bool)
     adata.obs['cluster'] = np.asarray(adata.obs['cluster']).astype(str)
     if not keep.all():
-        from .._anndata_lite import DeviceMatrix
+        from .._anndata_lite import DeviceMatrix, ShardedMatrix
         adata._inplace_subset_obs(keep)
-        if isinstance(adata.X, DeviceMatrix):
+        if isinstance(adata.X, (DeviceMatrix, ShardedMatrix)):
             st.Z = adata.X.tensor                    # the subset already happened on the device
         elif st.Z is not None:
             import torch

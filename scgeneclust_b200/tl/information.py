@@ -37,9 +37,9 @@ def _noise(n: int, random_state: int, target: bool):
 
 
 def _device_matrix(adata, st, attr: str, host) -> torch.Tensor:
-    from .._anndata_lite import DeviceMatrix
-    if isinstance(host, DeviceMatrix):
-        return host.tensor
+    from .._anndata_lite import DeviceMatrix, ShardedMatrix
+    if isinstance(host, (DeviceMatrix, ShardedMatrix)):
+        return host.tensor                      # ShardedMatrix: this rank's gene columns
     t = getattr(st, attr, None)
     if t is not None and tuple(t.shape) == tuple(np.shape(host)):
         return t
@@ -91,7 +91,10 @@ def find_relevant_genes(adata, top_pct: int, max_workers: int = os.cpu_count() -
     logger.info("Finding relevant genes...")
     st = get_state(adata)
     Z = _device_matrix(adata, st, 'Z', adata.X)
-    relevance = gene_relevance(Z, np.asarray(adata.obs['cluster']), random_state).cpu().numpy()
+    relevance = gene_relevance(Z, np.asarray(adata.obs['cluster']), random_state)
+    if st.comm is not None and st.comm.world > 1:
+        relevance = st.comm.all_gather_rows(relevance)          # every rank scored its own genes
+    relevance = relevance.cpu().numpy()
     logger.debug("Gene relevance computed!")
     rlv_th = np.percentile(relevance, 100 - top_pct)
     logger.opt(colors=True).debug(f"Relevance threshold: <yellow>{rlv_th}</yellow>")
@@ -99,8 +102,8 @@ def find_relevant_genes(adata, top_pct: int, max_workers: int = os.cpu_count() -
     adata._inplace_subset_var(is_relevant)
     adata.var['relevance'] = relevance[is_relevant]
     keep = torch.from_numpy(np.flatnonzero(is_relevant)).to(Z.device)
-    from .._anndata_lite import DeviceMatrix
-    st.Z = adata.X.tensor if isinstance(adata.X, DeviceMatrix) else Z.index_select(1, keep).contiguous()
+    from .._anndata_lite import DeviceMatrix, ShardedMatrix
+    st.Z = adata.X.tensor if isinstance(adata.X, (DeviceMatrix, ShardedMatrix)) else Z.index_select(1, keep).contiguous()
     if st.varm_pca is not None:
         st.varm_pca = st.varm_pca.index_select(0, keep).contiguous()
     logger.opt(colors=True).info(
@@ -130,7 +133,7 @@ def prepare_pair_roles(E: torch.Tensor, random_state: int = 0):
 
 
 def gene_redundancy(E: torch.Tensor, random_state: int = 0, p_begin: int = 0, p_end: Optional[int] = None,
-                    dense: bool = True, return_counts: bool = False, sorted_scan: bool = False):
+                    dense: bool = True, return_counts: bool = False, sorted_scan: bool = False, roles=None):
     """KSG MI of the gene pairs [p_begin, p_end) in `itertools.combinations(range(N), 2)` order - the values
     `_compute_redundancy` (scGeneClust/tl/information.py:60-63) returns.  Returns (condensed[p_end-p_begin],
     dense N x N symmetric or None[, nx, ny uint8 counts])."""
@@ -140,7 +143,7 @@ def gene_redundancy(E: torch.Tensor, random_state: int = 0, p_begin: int = 0, p_
     N, n = E.shape
     n_pairs = N * (N - 1) // 2
     p_end = n_pairs if p_end is None else p_end
-    XR, YR = prepare_pair_roles(E, random_state)
+    XR, YR = roles if roles is not None else prepare_pair_roles(E, random_state)
     cond = torch.empty(p_end - p_begin, dtype=torch.float64, device=dev)
     D = torch.zeros((N, N), dtype=torch.float64, device=dev) if dense else None
     nx = torch.empty((p_end - p_begin, n), dtype=torch.uint8, device=dev) if return_counts else None
@@ -160,14 +163,98 @@ def gene_redundancy(E: torch.Tensor, random_state: int = 0, p_begin: int = 0, p_
     return cond, D
 
 
+TILE_PAIRS = 4 * 1024 * 1024        # gene pairs per streamed tile (32 MB of float64 MI values)
+
+
+class _ForestBuffers:
+    """Ping-pong device buffers of a spanning forest (<= N - 1 weighted edges) + the Boruvka scratch."""
+
+    def __init__(self, N: int, device):
+        L = lib()
+        m = max(N - 1, 1)
+        self.N, self.dev = N, device
+        self.u = [torch.empty(m, dtype=torch.int32, device=device) for _ in range(2)]
+        self.v = [torch.empty(m, dtype=torch.int32, device=device) for _ in range(2)]
+        self.w = [torch.empty(m, dtype=torch.float64, device=device) for _ in range(2)]
+        self.n = [torch.zeros(1, dtype=torch.int32, device=device) for _ in range(2)]
+        self.scratch = torch.empty(L.mst_scratch_bytes(N), dtype=torch.uint8, device=device)
+        self.cur, self.count = 0, 0
+
+    def fold(self, cond: Optional[torch.Tensor], p_begin: int, extra=None):
+        """forest <- MSF(forest u condensed tile [p_begin, p_begin + len(cond)) u extra edges (u, v, w tensors))."""
+        L, stream = lib(), stream_handle()
+        c, o = self.cur, self.cur ^ 1
+        if extra is not None:
+            eu = torch.cat([self.u[c][:self.count], extra[0]]).contiguous()
+            ev = torch.cat([self.v[c][:self.count], extra[1]]).contiguous()
+            ew = torch.cat([self.w[c][:self.count], extra[2]]).contiguous()
+        else:
+            eu, ev, ew = self.u[c], self.v[c], self.w[c]
+        n_extra = self.count + (0 if extra is None else int(extra[0].numel()))
+        n_cond = 0 if cond is None else int(cond.numel())
+        L.mst_boruvka_edges(ptr(cond), p_begin, n_cond, ptr(eu), ptr(ev), ptr(ew), n_extra, self.N, ptr(self.u[o]),
+                            ptr(self.v[o]), ptr(self.w[o]), ptr(self.n[o]), ptr(self.scratch), stream)
+        self.cur = o
+        self.count = int(self.n[o].item())
+
+    def edges(self):
+        c = self.cur
+        return self.u[c][:self.count], self.v[c][:self.count], self.w[c][:self.count]
+
+
+def redundancy_forest(E: torch.Tensor, random_state: int = 0, comm=None, tile_pairs: int = TILE_PAIRS):
+    """Maximum-redundancy spanning forest of the relevant genes WITHOUT the N x N matrix (north_star: "no dense N x N
+    materialisation ... top-k merge"): the KSG MI values of the gene pairs are produced tile by tile (gc_mi_cc_pairs)
+    and each tile is folded into the forest found so far (gc_mst_boruvka_edges; MSF(E1 u E2) = MSF(MSF(E1) u E2)).
+    With a gene-shard communicator every rank streams its own slice of the pair range, the per-rank forests
+    (<= N - 1 edges each) are all-gathered and reduced once more, identically on every rank.
+    Returns (edges int64 (n, 2) sorted by (source, target), weights float64 (n,), n_pairs)."""
+    require_cuda()
+    dev = E.device
+    N = E.shape[0]
+    n_pairs = N * (N - 1) // 2
+    lo, hi = (0, n_pairs) if comm is None or comm.world == 1 else comm.split_range(n_pairs)
+    roles = prepare_pair_roles(E, random_state)
+    forest = _ForestBuffers(N, dev)
+    for t0 in range(lo, hi, tile_pairs):
+        t1 = min(hi, t0 + tile_pairs)
+        cond, _ = gene_redundancy(E, random_state, t0, t1, dense=False, roles=roles)
+        forest.fold(cond, t0)
+    if comm is not None and comm.world > 1:
+        import torch.distributed as dist
+        m = max(N - 1, 1)
+        u, v, w = forest.edges()
+        pack = torch.zeros((m, 3), dtype=torch.float64, device=dev)           # weight 0 = padding (a non-edge)
+        pack[:forest.count, 0], pack[:forest.count, 1], pack[:forest.count, 2] = u.double(), v.double(), w
+        parts = [torch.empty_like(pack) for _ in range(comm.world)]
+        dist.all_gather(parts, pack, group=comm.group)
+        allp = torch.cat(parts)
+        merged = _ForestBuffers(N, dev)
+        merged.fold(None, 0, extra=(allp[:, 0].to(torch.int32).contiguous(), allp[:, 1].to(torch.int32).contiguous(),
+                                    allp[:, 2].contiguous()))
+        forest = merged
+    u, v, w = forest.edges()
+    e = torch.stack([u, v], 1).cpu().numpy().astype(np.int64)
+    wh = w.cpu().numpy()
+    order = np.lexsort((e[:, 1], e[:, 0]))
+    return e[order], wh[order], n_pairs
+
+
 def compute_gene_redundancy(adata, max_workers: int = os.cpu_count() - 1, random_state: int = 0):
     """scGeneClust/tl/information.py:66-85: `varp['redundancy']` = symmetric N x N float64, zero diagonal.  With a
-    gene-shard communicator in the state, ranks compute disjoint condensed ranges and all-gather them."""
+    gene-shard communicator in the state, ranks compute disjoint condensed ranges and all-gather them.
+    When the entry point does not have to hand the matrix back (`return_info=False`) it is never built: the MI tiles are
+    folded straight into the spanning forest the next stage needs (`redundancy_forest`), which is kept in the state."""
     logger.info("Computing gene redundancy...")
     st = get_state(adata)
     E = _device_matrix(adata, st, 'varm_pca', adata.varm['X_pca'])
     N = E.shape[0]
     comm = st.comm
+    if not st.dense_redundancy:
+        st.forest = redundancy_forest(E, random_state, comm)[:2]
+        st.redundancy = None
+        logger.info("Gene redundancy computed (streamed into the spanning forest; no N x N matrix).")
+        return
     if comm is None or comm.world == 1:
         _, D = gene_redundancy(E, random_state)
     else:
@@ -180,6 +267,7 @@ def compute_gene_redundancy(adata, max_workers: int = os.cpu_count() - 1, random
         D[iu[0], iu[1]] = full
         D = D + D.t()
     st.redundancy = D
+    st.forest = None
     from .._anndata_lite import AnnDataLite, DeviceMatrix
     # 8 N^2 bytes (128 MB at N = 4000): stays on the device for the MST and the edge scaling; downloaded when read
     adata.varp['redundancy'] = DeviceMatrix(D) if isinstance(adata, AnnDataLite) else D.cpu().numpy()
@@ -286,12 +374,26 @@ def compute_gene_complementarity(adata, max_workers: int = os.cpu_count() - 1, r
     st = get_state(adata)
     logger.debug("Building MST...")
     D = st.redundancy
-    if D is not None and tuple(D.shape) == tuple(np.shape(adata.varp['redundancy'])):
+    if st.forest is not None:                                   # streamed: the forest came out of the redundancy stage
+        adata.uns['mst_edges'] = st.forest[0]
+    elif D is not None and tuple(D.shape) == tuple(np.shape(adata.varp['redundancy'])):
         adata.uns['mst_edges'] = redundancy_mst_device(D)
     else:
         adata.uns['mst_edges'] = redundancy_mst(np.asarray(adata.varp['redundancy']))
     logger.debug("MST built.")
-    Z = _device_matrix(adata, st, 'Z', adata.X)
-    adata.uns['mst_edges_complm'] = gene_complementarity(Z, np.asarray(adata.obs['cluster']), adata.uns['mst_edges'],
-                                                         random_state)
+    from .._anndata_lite import ShardedMatrix
+    edges = adata.uns['mst_edges']
+    clusters = np.asarray(adata.obs['cluster'])
+    comm = st.comm
+    if isinstance(adata.X, ShardedMatrix) and comm is not None and comm.world > 1:
+        # the two genes of an edge may live on different ranks: the residual columns of the RELEVANT genes (cells x N,
+        # small) are all-gathered, the edges are split across the ranks and their values gathered
+        Z = adata.X.gather_columns()
+        lo, hi = comm.split_range(len(edges))
+        local = gene_complementarity(Z, clusters, edges[lo:hi], random_state) if hi > lo else np.zeros(0)
+        cm = comm.all_gather_ranges(torch.from_numpy(np.ascontiguousarray(local)).to(Z.device), len(edges))
+        adata.uns['mst_edges_complm'] = cm.cpu().numpy()
+    else:
+        Z = _device_matrix(adata, st, 'Z', adata.X)
+        adata.uns['mst_edges_complm'] = gene_complementarity(Z, clusters, edges, random_state)
     logger.info("Gene complementarity computed.")

@@ -52,9 +52,45 @@ def _worker(rank, world, port, total):
         plo, phi = comm.split_range(n_pairs)
         vec = torch.arange(n_pairs, dtype=torch.float64)
         assert torch.equal(comm.all_gather_ranges(vec[plo:phi].clone(), n_pairs), vec)
+        # row-sliced cell-space panel: reduce-scatter of the partial sums, all-gather of the processed chunks
+        n_rows = 41
+        chunk = comm.row_chunk(n_rows)
+        assert chunk == 21
+        partial = torch.zeros((chunk * world, 4), dtype=torch.float32)
+        partial[:n_rows] = torch.from_numpy(rs.standard_normal((2, n_rows, 4)).astype(np.float32))[rank]
+        both = torch.from_numpy(np.random.RandomState(0).standard_normal((40, total)).astype(np.float32))  # same stream as above
+        mine = torch.empty((chunk, 4), dtype=torch.float32)
+        expect = partial.clone()
+        dist.all_reduce(expect)
+        comm.reduce_scatter_rows(partial.clone(), mine)
+        assert torch.equal(mine, expect[rank * chunk:(rank + 1) * chunk])
+        gathered = torch.empty((chunk * world, 4), dtype=torch.float32)
+        comm.all_gather_chunks(mine * 2.0, gathered)
+        assert torch.equal(gathered, expect * 2.0)
+        # flags raised on one rank reach every rank (rank-consistent errors)
+        flag = torch.tensor([0, 1 if rank == 1 else 0], dtype=torch.int32)
+        assert comm.all_reduce_max(flag).tolist() == [0, 1]
         comm.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _worker_too_few_genes(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            GeneShardComm(64)              # 64 genes over 2 ranks: the second shard would be empty
+        except ValueError as exc:
+            assert "cannot be split" in str(exc)
+        else:
+            raise AssertionError("empty shard accepted")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_empty_shard_rejected_on_every_rank():
+    mp.spawn(_worker_too_few_genes, args=(2, _free_port()), nprocs=2, join=True)
 
 
 def test_gene_shard_comm_gloo_world2():

@@ -19,10 +19,10 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _torchrun(extra, nproc=2, timeout=900):
+def _torchrun(extra, nproc=2, timeout=900, script="check_sharded_parity.py"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "scripts", "check_sharded_parity.py"), *extra]
+           os.path.join(ROOT, "scripts", script), *extra]
     res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
     print(res.stdout[-3000:])
     return res
@@ -54,3 +54,16 @@ def test_two_ranks_nccl_sharded_equals_single():
         pytest.skip("needs 2 GPUs (NCCL refuses two ranks on one device); the gloo variant above covers the code path")
     res = _torchrun(["20000", "6000", "--backend", "nccl"])
     assert res.returncode == 0, res.stdout[-2000:]
+
+
+def test_two_ranks_geneclust_ps_sharded_equals_single():
+    """BASELINE.json config c4's entry: `scGeneClust(version='ps')` on gene-sharded host counts under torchrun - relevance
+    per gene shard, pair ranges streamed into per-rank forests and merged, complementarity split by edges - selects the
+    same genes as the single-GPU run."""
+    torch = _need_cuda()
+    if torch.cuda.device_count() >= 2:
+        res = _torchrun(["3000", "2500", "--backend", "nccl"], script="check_sharded_ps.py")
+    else:
+        res = _torchrun(["3000", "2500", "--backend", "gloo", "--same-device"], script="check_sharded_ps.py")
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert "identical to single GPU: True" in res.stdout

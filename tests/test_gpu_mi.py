@@ -237,3 +237,46 @@ def test_device_mst_equals_total_order_kruskal(torch_cuda, N, zero_frac, ties):
     assert np.isclose(R[got[:, 0], got[:, 1]].sum(), R[sp_edges[:, 0], sp_edges[:, 1]].sum(), rtol=1e-12)
     if not ties:
         assert np.array_equal(got, sp_edges)
+
+
+@pytest.mark.parametrize("N,tile,ties", [(64, 500, False), (700, 50_000, True), (1500, 300_000, False)])
+def test_streamed_forest_equals_dense_forest(torch_cuda, N, tile, ties):
+    """`redundancy_forest` (MI tiles folded into the spanning forest by gc_mst_boruvka_edges; no N x N matrix) finds the
+    forest the dense routine finds on the materialised matrix - same edges, and the weights it carries are the matrix
+    entries - for tile sizes that split the pair range unevenly; with many exactly equal MI values too (a coarse
+    embedding makes ties), where only the shared strict edge order makes the forest unique."""
+    torch = torch_cuda
+    from scgeneclust_b200.tl.information import gene_redundancy, redundancy_forest, redundancy_mst_device
+    rs = np.random.RandomState(N)
+    E = (rs.standard_normal((N, 50)) * (3.0 / (1 + np.arange(50)))).astype(np.float32)
+    if ties:
+        E = np.round(E, 1)                                   # few distinct coordinates: many tied MI values
+    Ed = torch.from_numpy(E).cuda()
+    _, D = gene_redundancy(Ed, 0)
+    ref = redundancy_mst_device(D)
+    edges, weights, n_pairs = redundancy_forest(Ed, 0, None, tile_pairs=tile)
+    assert n_pairs == N * (N - 1) // 2
+    assert np.array_equal(edges, ref)
+    assert np.array_equal(weights, D.cpu().numpy()[edges[:, 0], edges[:, 1]])
+
+
+def test_ps_entry_streamed_equals_dense(torch_cuda):
+    """`scGeneClust(version='ps')` without return_info streams the redundancy stage (no varp['redundancy']); the selected
+    genes equal those of the return_info=True run, which builds the dense matrix like the reference."""
+    from oracle.synth import cell_types, synth_counts
+    from scgeneclust_b200 import AnnDataLite, scGeneClust
+    from scgeneclust_b200.synth import synth_params
+    p = synth_params(900, 0)
+    X = synth_counts(p, 0, 1300, 0, 900)
+    keep = (X > 0).sum(0) >= 3
+    X = np.ascontiguousarray(X[:, keep]).astype(np.float32)
+    names = np.array([f"g{i}" for i in np.flatnonzero(keep)], dtype=object)
+
+    def make():
+        ad = AnnDataLite(X, var_names=names)
+        ad.obs['cluster'] = np.array([f"type{t}" for t in cell_types(p, 0, 1300)])
+        return ad
+    info, genes_dense = scGeneClust(make(), version='ps', n_obs_clusters=8, return_info=True, verbosity=0)
+    genes_stream = scGeneClust(make(), version='ps', n_obs_clusters=8, verbosity=0)
+    assert 'redundancy' in info.varp
+    assert np.array_equal(genes_dense, genes_stream)
