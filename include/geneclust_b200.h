@@ -169,6 +169,17 @@ int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, int K, int32
 int gc_searchsorted_right(const double *cdf, int64_t n, const double *u, int m, int32_t *idx, void *stream);
 /* out[0] = float64 sum of a float32 vector in a fixed order (batch inertia, cluster/_k_means_common.pyx:94-124). */
 int gc_sum_f32(const float *v, int64_t n, double *out, void *stream);
+/* One step of MiniBatchKMeans.fit (sklearn cluster/_kmeans.py:2169-2196, reached from scGeneClust/tl/cluster.py:70) as one
+ * call: idx = searchsorted(cdf, u, 'right') (the host's uniform draws -> batch rows), assignment of X[idx] to `centers`,
+ * *inertia = sum of the squared distances (float64), running-mean update into centers_new / counts. */
+int gc_kmeans_minibatch_step(const float *X, int64_t ldx, int64_t n, int d, int K, const double *cdf, const double *u,
+                             int batch, int32_t *idx, int32_t *labels_b, float *sq_b, const float *centers,
+                             float *centers_new, float *counts, double *inertia, void *stream);
+/* Random reassignment of starved centres (cluster/_kmeans.py:1655-1682): centers_new[clusters[r]] = X[idx[picks[r]]],
+ * counts[clusters[r]] = min_count, r < n_reassign (clusters / picks: device int32). */
+int gc_kmeans_reassign(const float *X, int64_t ldx, int d, const int32_t *idx, const int32_t *clusters,
+                       const int32_t *picks, int n_reassign, float min_count, float *centers_new, float *counts,
+                       void *stream);
 /* dist[s] = |x_s - centers[labels[s]]|_2 (paired_distances, scGeneClust/tl/cluster.py:101). */
 int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, const float *centers, const int32_t *labels,
                    float *dist, void *stream);

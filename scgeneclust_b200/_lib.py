@@ -58,6 +58,8 @@ SIGNATURES = {
     "gc_kmeanspp_init": (C.c_int, [_p, _i64, _i64, C.c_int, C.c_int, _i32, _p, C.c_int, _p, _p, _p, _p]),
     "gc_searchsorted_right": (C.c_int, [_p, _i64, _p, C.c_int, _p, _p]),
     "gc_sum_f32": (C.c_int, [_p, _i64, _p, _p]),
+    "gc_kmeans_minibatch_step": (C.c_int, [_p, _i64, _i64, C.c_int, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gc_kmeans_reassign": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, C.c_int, _f32, _p, _p, _p]),
     "gc_paired_dist": (C.c_int, [_p, _i64, _i64, C.c_int, _p, _p, _p, _p]),
     "gc_closeness": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gc_binomial_deviance_scratch_bytes": (_i64, [_i64, C.c_int]),

@@ -607,6 +607,17 @@ __global__ void searchsorted_right_kernel(const double *__restrict__ cdf, int64_
     idx[i] = (int32_t)lo;
 }
 
+// random reassignment of starved centres (_mini_batch_step, cluster/_kmeans.py:1655-1682): centre clusters[r] <- the batch
+// sample picks[r] (a position in the mini-batch, i.e. row idx[picks[r]] of X), its count <- min_count
+__global__ void kmeans_reassign_kernel(const float *__restrict__ X, int64_t ldx, int d, const int32_t *__restrict__ idx,
+                                       const int32_t *__restrict__ clusters, const int32_t *__restrict__ picks,
+                                       float min_count, float *__restrict__ centers_new, float *__restrict__ counts) {
+    const int r = blockIdx.x, c = clusters[r];
+    const float *src = X + (int64_t)idx[picks[r]] * ldx;
+    for (int f = threadIdx.x; f < d; f += blockDim.x) centers_new[(int64_t)c * d + f] = src[f];
+    if (threadIdx.x == 0) counts[c] = min_count;
+}
+
 // deterministic float64 sum of a float32 vector (single CTA, fixed tree), result as float64 and float32
 __global__ void __launch_bounds__(1024) sum_f32_kernel(const float *__restrict__ v, int64_t n, double *out) {
     __shared__ double red[1024];
@@ -697,6 +708,27 @@ extern "C" int gc_searchsorted_right(const double *cdf, int64_t n, const double 
     GC_REQUIRE(cdf && u && idx && n >= 1 && m >= 1, "bad arguments");
     searchsorted_right_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, as_stream(stream)>>>(cdf, n, u, m, idx);
     return check_launch("searchsorted_right_kernel");
+}
+
+extern "C" int gc_kmeans_minibatch_step(const float *X, int64_t ldx, int64_t n, int d, int K, const double *cdf,
+                                        const double *u, int batch, int32_t *idx, int32_t *labels_b, float *sq_b,
+                                        const float *centers, float *centers_new, float *counts, double *inertia,
+                                        void *stream) {
+    // one `_mini_batch_step` of MiniBatchKMeans.fit (cluster/_kmeans.py:2169-2196) as ONE call: the batch indices from the
+    // host's uniform draws, assignment to the current centres, batch inertia, running-mean update of the centres
+    if (int rc = gc_searchsorted_right(cdf, n, u, batch, idx, stream)) return rc;
+    if (int rc = gc_kmeans_assign(X, ldx, idx, batch, centers, K, d, labels_b, sq_b, stream)) return rc;
+    if (int rc = gc_sum_f32(sq_b, batch, inertia, stream)) return rc;
+    return gc_kmeans_minibatch_update(X, ldx, idx, batch, labels_b, centers, centers_new, counts, K, d, stream);
+}
+
+extern "C" int gc_kmeans_reassign(const float *X, int64_t ldx, int d, const int32_t *idx, const int32_t *clusters,
+                                  const int32_t *picks, int n_reassign, float min_count, float *centers_new, float *counts,
+                                  void *stream) {
+    GC_REQUIRE(X && idx && clusters && picks && centers_new && counts && d >= 1, "bad arguments");
+    if (n_reassign <= 0) return 0;
+    kmeans_reassign_kernel<<<n_reassign, 64, 0, as_stream(stream)>>>(X, ldx, d, idx, clusters, picks, min_count, centers_new, counts);
+    return check_launch("kmeans_reassign_kernel");
 }
 
 extern "C" int gc_sum_f32(const float *v, int64_t n, double *out, void *stream) {

@@ -37,6 +37,10 @@ namespace gc {
 #ifndef TS_A_STAGES_N
 #define TS_A_STAGES_N 5
 #endif
+#ifndef TS_I2F_WORDS_N      // of the 4 count words (8 entries) of a chunk, how many are converted by I2F.U16 (XU pipe)
+#define TS_I2F_WORDS_N 2
+#endif
+constexpr int TS_I2F_WORDS = TS_I2F_WORDS_N;
 constexpr int TS_GROUPS = TS_GROUPS_N;                           // producer groups of four warps
 constexpr int TS_A_STAGES = TS_A_STAGES_N;                       // A-operand slots in tensor memory (64 columns each)
 constexpr int TS_PRODUCER_WARPS = 4 * TS_GROUPS;
@@ -55,6 +59,23 @@ constexpr int TS_ACC_COLS = 192, TS_A_COLS = 64;   // D1 = [0, 128): A_hi [Q_hi 
 static_assert(TS_ACC_COLS + TS_A_STAGES * TS_A_COLS <= TC_TMEM_COLS, "TMEM budget");
 static_assert(TS_GROUPS >= 4, "the epilogue uses sixteen producer warps");
 static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared-memory budget");
+
+// mbarrier wait that lets the HARDWARE park the warp: try_wait with a suspend-time hint returns only when the phase
+// completed or the hint ran out, so a waiting warp issues a handful of instructions per microsecond instead of a
+// try_wait / nanosleep / branch loop (the kernel is instruction-issue bound: polling loops of the waiting warps were 15 %
+// of all issued instructions).  Bounded: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+        if (spin > (1u << 20)) __trap();
+    }
+}
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -224,7 +245,10 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         //          chunk c ^ (m & 7) - eight consecutive lanes read eight different bank groups.
         // TRANS 1: raw tile = 64 cells x 128 genes, 256-byte rows, no swizzle: a warp reads 32 consecutive uint16.
         const uint32_t row_off = TRANS == 0 ? (uint32_t)m * 128u : (uint32_t)m * 2u;
-        const uint32_t swz = TRANS == 0 ? (uint32_t)(m & 7) : 0u;
+        // TRANS 0: byte offsets of this row's eight swizzled 16-byte chunks inside a raw tile, computed once
+        uint32_t chunk_off[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) chunk_off[c] = row_off + ((((uint32_t)c) ^ (uint32_t)(m & 7)) << 4);
         for (int it = group; it < n_it; it += TS_GROUPS) {
             const int rs = it % TS_RAW_STAGES;                    // raw slot of this stage (the TMA runs ahead of the groups)
             // TMEM A slot of this stage.  There are more slots than groups: the slot was last used by stage it - TS_A_STAGES,
@@ -232,9 +256,10 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             // group every group waited for its own, most recently issued, UMMAs: 32 % of all stall samples)
             const int as = it % TS_A_STAGES;
             const uint32_t a_col = a_lane + (uint32_t)as * TS_A_COLS;
-            const uint32_t raw_row = smem_base + rs * TS_RAW_BYTES + row_off;
+            const uint32_t raw_tile = smem_base + rs * TS_RAW_BYTES;
+            const uint32_t raw_row = raw_tile + row_off;
             const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
-            mbar_wait_backoff(bar_raw_full + 8 * rs, (uint32_t)(it / TS_RAW_STAGES) & 1);
+            mbar_wait_park(bar_raw_full + 8 * rs, (uint32_t)(it / TS_RAW_STAGES) & 1);
 #pragma unroll
             for (int c2 = 0; c2 < TC_TK / 16; ++c2) {             // 16 entries (k = 16 c2 .. 16 c2 + 15) per round
                 uint32_t hi[8], lo[8];
@@ -247,13 +272,22 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                                          __uint_as_float(k1.z), __uint_as_float(k1.w)};
                     float z[8];
                     if constexpr (TRANS == 0) {
-                        const uint4 raw = lds128(raw_row + (((uint32_t)c ^ swz) << 4));
+                        const uint4 raw = lds128(raw_tile + chunk_off[c]);
                         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
-                            // exact uint16 -> float: splice the 16 bits under the 2^23 exponent, subtract 2^23
-                            const float x0 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7410)) - 8388608.0f;
-                            const float x1 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7432)) - 8388608.0f;
+                            // exact uint16 -> float.  Two ways, mixed to balance the pipes: splice the 16 bits under the
+                            // 2^23 exponent and subtract 2^23 (PRMT on the ALU pipe + FADD: two issue slots), or one
+                            // I2F.U16 with a half-word selector (one issue slot, but on the quarter-rate XU pipe that
+                            // also runs the MUFU.RSQ of every entry)
+                            float x0, x1;
+                            if (p < TS_I2F_WORDS) {
+                                x0 = (float)(unsigned short)(w[p] & 0xffffu);
+                                x1 = (float)(unsigned short)(w[p] >> 16);
+                            } else {
+                                x0 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7410)) - 8388608.0f;
+                                x1 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7432)) - 8388608.0f;
+                            }
                             z[2 * p] = resid1<LO_CLIP>(x0, fixed * kc[2 * p], a.inv_theta, a.clip);
                             z[2 * p + 1] = resid1<LO_CLIP>(x1, fixed * kc[2 * p + 1], a.inv_theta, a.clip);
                         }
@@ -261,7 +295,8 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const uint32_t v = lds_u16(raw_row + (uint32_t)(c * 8 + e) * 256u);
-                            const float xf = __uint_as_float(v | a.magic) - 8388608.0f;
+                            const float xf = e < 2 * TS_I2F_WORDS ? (float)(unsigned short)v
+                                                                  : __uint_as_float(v | a.magic) - 8388608.0f;
                             z[e] = resid1<LO_CLIP>(xf, fixed * kc[e], a.inv_theta, a.clip);
                         }
                     }
@@ -270,7 +305,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 }
                 if (c2 == 0) {
                     // the TMEM slot was last read by the UMMAs of this group's previous stage
-                    mbar_wait_backoff(bar_a_empty + 8 * as, ((uint32_t)(it / TS_A_STAGES) & 1) ^ 1);   // passes at once on the first lap
+                    mbar_wait_park(bar_a_empty + 8 * as, ((uint32_t)(it / TS_A_STAGES) & 1) ^ 1);   // passes at once on the first lap
                     tc_fence_after();
                 }
                 tmem_st8(a_col + 8 * c2, hi);                     // 16 bf16 = 8 columns
@@ -286,7 +321,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 
         // =============================== epilogue ===============================
         if (n_it > 0) {
-            mbar_wait(bar_accum, 0);
+            mbar_wait_park(bar_accum, 0);
             tc_fence_after();
         }
         if (warp < 16 && warp < TS_PRODUCER_WARPS) {
@@ -325,8 +360,8 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
         for (int it = 0; it < n_it; ++it) {
             const int s = it % TS_A_STAGES, sb = it % TS_B_STAGES;
-            mbar_wait(bar_b_full + 8 * sb, (uint32_t)(it / TS_B_STAGES) & 1);
-            mbar_wait(bar_a_full + 8 * s, (uint32_t)(it / TS_A_STAGES) & 1);
+            mbar_wait_park(bar_b_full + 8 * sb, (uint32_t)(it / TS_B_STAGES) & 1);
+            mbar_wait_park(bar_a_full + 8 * s, (uint32_t)(it / TS_A_STAGES) & 1);
             tc_fence_after();
             umma_stage_ts(tmem_u, tmem_u + TS_ACC_COLS + (uint32_t)s * TS_A_COLS,
                           b_low0 + (uint32_t)sb * (TS_PANEL_BYTES >> 4), b_hiw, idesc128, idesc64, it > 0 ? 1u : 0u,
@@ -342,7 +377,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             for (int it = 0; it < n_it; ++it) {
                 const int s = it % TS_RAW_STAGES;
                 const int32_t kk = (int32_t)(k_lo + (int64_t)it * TC_TK);
-                mbar_wait_backoff(bar_raw_empty + 8 * s, ((uint32_t)(it / TS_RAW_STAGES) & 1) ^ 1);
+                mbar_wait_park(bar_raw_empty + 8 * s, ((uint32_t)(it / TS_RAW_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_raw_full + 8 * s, TS_RAW_BYTES + TS_KC_BYTES);
                 if (TRANS == 0) tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, kk, (int32_t)m0, bar_raw_full + 8 * s, policy);
                 else tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, (int32_t)m0, kk, bar_raw_full + 8 * s, policy);
@@ -357,7 +392,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
             const char *ql = reinterpret_cast<const char *>(a.Ql) + (k_lo / TC_TK) * TC_B_BYTES;
             for (int it = 0; it < n_it; ++it) {
                 const int sb = it % TS_B_STAGES;
-                mbar_wait_backoff(bar_b_empty + 8 * sb, ((uint32_t)(it / TS_B_STAGES) & 1) ^ 1);
+                mbar_wait_park(bar_b_empty + 8 * sb, ((uint32_t)(it / TS_B_STAGES) & 1) ^ 1);
                 const uint32_t b_hi = smem_base + TS_OFF_PANEL + sb * TS_PANEL_BYTES;
                 mbar_arrive_expect_tx(bar_b_full + 8 * sb, TS_PANEL_BYTES);
                 bulk_g2s(b_hi, qh + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);

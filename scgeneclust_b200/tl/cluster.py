@@ -14,6 +14,17 @@ from .._lib import lib, ptr, require_cuda, stream_handle
 from ..pp._preprocessing import get_state
 
 
+_PINNED: dict = {}
+
+
+def _pinned(name: str, n: int, dtype) -> torch.Tensor:
+    """Process-wide pinned staging buffers (cudaHostAlloc costs ~0.1 ms a call, more than a mini-batch step)."""
+    key = (name, int(n), dtype)
+    if key not in _PINNED:
+        _PINNED[key] = torch.empty(int(n), dtype=dtype).pin_memory()
+    return _PINNED[key]
+
+
 class DeviceMiniBatchKMeans:
     """`sklearn.cluster.MiniBatchKMeans(n_clusters, batch_size, random_state, n_init='auto')` as the reference
     configures it (scGeneClust/tl/cluster.py:66-69), re-expressed for the device.
@@ -91,29 +102,29 @@ class DeviceMiniBatchKMeans:
         sq_b = torch.empty(batch, dtype=torch.float32, device=dev)
         inertia_d = torch.empty(1, dtype=torch.float64, device=dev)
         idx = torch.empty(batch, dtype=torch.int32, device=dev)
-        # pinned staging: one upload and one (two-part) read-back per step, a single stream synchronisation
-        u_pin = torch.empty(batch, dtype=torch.float64).pin_memory()
+        # pinned staging: per step one upload of the uniforms, one (two-part) read-back, one stream synchronisation and -
+        # when starved centres are reassigned - one upload of (cluster ids, picked batch positions)
+        u_pin = _pinned('u', batch, torch.float64)
         u_dev = torch.empty(batch, dtype=torch.float64, device=dev)
         cdf_dev = torch.from_numpy(cdf).to(dev)
-        counts_pin = torch.empty(K, dtype=torch.float32).pin_memory()
-        inertia_pin = torch.empty(1, dtype=torch.float64).pin_memory()
+        counts_pin = _pinned('counts', K, torch.float32)
+        inertia_pin = _pinned('inertia', 1, torch.float64)
+        re_pin = _pinned('reassign', 2 * K, torch.int32)
+        re_dev = torch.empty(2 * K, dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream()
         step = 0
         for step in range(n_steps):
             # the uniform draws go up, the searchsorted runs on the device against the same float64 cdf
             u_pin.numpy()[:] = rs.random_sample(batch)
             u_dev.copy_(u_pin, non_blocking=True)
-            L.searchsorted_right(ptr(cdf_dev), n, ptr(u_dev), batch, ptr(idx), st)
             # _random_reassign(), evaluated before the step on the counts of the previous one
             n_since_reassign += batch
             random_reassign = bool((counts_h == 0).any() or n_since_reassign >= 10 * K)
             if random_reassign:
                 n_since_reassign = 0
-            # _mini_batch_step
-            L.kmeans_assign(ptr(X), X.stride(0), ptr(idx), batch, ptr(centers), K, d, ptr(labels_b), ptr(sq_b), st)
-            L.sum_f32(ptr(sq_b), batch, ptr(inertia_d), st)
-            L.kmeans_minibatch_update(ptr(X), X.stride(0), ptr(idx), batch, ptr(labels_b), ptr(centers),
-                                      ptr(centers_new), ptr(counts), K, d, st)
+            # _mini_batch_step: one call enqueues batch selection, assignment, inertia and centre update
+            L.kmeans_minibatch_step(ptr(X), X.stride(0), n, d, K, ptr(cdf_dev), ptr(u_dev), batch, ptr(idx), ptr(labels_b),
+                                    ptr(sq_b), ptr(centers), ptr(centers_new), ptr(counts), ptr(inertia_d), st)
             counts_pin.copy_(counts, non_blocking=True)
             inertia_pin.copy_(inertia_d, non_blocking=True)
             stream.synchronize()
@@ -127,13 +138,15 @@ class DeviceMiniBatchKMeans:
                 n_reassigns = int(to_reassign.sum())
                 if n_reassigns:
                     picks = rs.choice(batch, replace=False, size=n_reassigns)
-                    rows = idx.index_select(0, torch.from_numpy(picks.astype(np.int64)).to(dev)).to(torch.int64)
-                    centers_new[torch.from_numpy(np.flatnonzero(to_reassign)).to(dev)] = X.index_select(0, rows)
-                    # the "dirty hack" count reset of _mini_batch_step (cluster/_kmeans.py:1679-1682); a no-op without
-                    # reassigned centres
-                    counts_h[to_reassign] = np.min(counts_h[~to_reassign])
-                    counts_pin.numpy()[:] = counts_h
-                    counts.copy_(counts_pin, non_blocking=True)
+                    # the "dirty hack" count reset of _mini_batch_step (cluster/_kmeans.py:1679-1682)
+                    min_count = np.min(counts_h[~to_reassign])
+                    counts_h[to_reassign] = min_count
+                    re_np = re_pin.numpy()
+                    re_np[:n_reassigns] = np.flatnonzero(to_reassign)
+                    re_np[K:K + n_reassigns] = picks
+                    re_dev.copy_(re_pin, non_blocking=True)
+                    L.kmeans_reassign(ptr(X), X.stride(0), d, ptr(idx), ptr(re_dev), ptr(re_dev[K:]), n_reassigns,
+                                      float(min_count), ptr(centers_new), ptr(counts), st)
             centers, centers_new = centers_new, centers
             # _mini_batch_convergence (tol == 0)
             batch_inertia /= batch
@@ -210,7 +223,12 @@ def generate_gene_clusters(adata):
     g1, g2 = adata.uns['mst_edges'][:, 0], adata.uns['mst_edges'][:, 1]
     rel = adata.var['relevance'].values
     edge_min_relevance = np.minimum(rel[g1], rel[g2])
-    edge_redundancy = adata.varp['redundancy'][g1, g2]        # device-backed matrices gather the N - 1 entries there
+    forest = get_state(adata).forest
+    if forest is not None:                                    # streamed redundancy stage: the forest carries its weights
+        assert np.array_equal(forest[0], adata.uns['mst_edges'])
+        edge_redundancy = forest[1]
+    else:
+        edge_redundancy = adata.varp['redundancy'][g1, g2]    # device-backed matrices gather the N - 1 entries there
     edge_scales = np.maximum(edge_min_relevance, adata.uns['mst_edges_complm']) / edge_redundancy
     MST = np.hstack((adata.uns['mst_edges'], edge_scales.reshape(-1, 1)))
     MST = MST[np.argsort(MST.T[2]), :]
