@@ -68,8 +68,9 @@ int gc_dense_to_counts(const float *src, int64_t ld_src, int64_t n_rows, int64_t
  * ------------------------------------------------------------------------------------------------------- */
 /* Exact integer row sums (per cell, C), column sums (per gene, G) of counts[C x G]; outputs are uint64 and
  * are ACCUMULATED into (zero them first), so a gene-sharded caller can all-reduce row sums. */
+/* col_max (G x uint32, zeroed by the caller, or NULL): the largest count of every gene. */
 int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, unsigned long long *row_sum,
-                  unsigned long long *col_sum, void *stream);
+                  unsigned long long *col_sum, uint32_t *col_max, void *stream);
 /* Materialise Z (float32, C x G, leading dimension ldz) - used by the ps path, which needs adata.X = residuals
  * (scGeneClust/tl/information.py:46,119), and by tests. */
 int gc_pearson_residuals(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, const float *row_sum_f,
@@ -95,6 +96,8 @@ typedef struct {
     const float *row_sum_f, *col_sum_f; float total, theta, clip;
     const float *row_shift;   /* C or NULL */
     const float *col_shift;   /* G or NULL */
+    int32_t upper_clip_inactive;   /* != 0: the caller has PROVED that no residual reaches +clip (gc_count_sums col_max:
+                                    * max_g x_max(g) / sqrt(r_min s_g / T) < clip), so gc_rsvd_apply may skip the test */
 } gc_residual_matrix;
 
 int64_t gc_rsvd_scratch_bytes(int64_t C, int64_t G);

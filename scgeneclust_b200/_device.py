@@ -174,6 +174,7 @@ class ResidualOperator:
     total: float
     theta: float
     clip: float
+    upper_clip_inactive: bool = False      # proved from the data: no residual reaches +clip (see from_counts)
     _scratch: Optional[torch.Tensor] = field(default=None, repr=False)
 
     @property
@@ -193,7 +194,9 @@ class ResidualOperator:
         dev = counts.device
         row_sum = torch.zeros(counts.C, dtype=torch.int64, device=dev)
         col_sum = torch.zeros(counts.G, dtype=torch.int64, device=dev)
-        L.count_sums(ptr(counts.data), counts.C, counts.G, counts.ld, ptr(row_sum), ptr(col_sum), stream_handle())
+        col_max = torch.zeros(counts.G, dtype=torch.int32, device=dev)
+        L.count_sums(ptr(counts.data), counts.C, counts.G, counts.ld, ptr(row_sum), ptr(col_sum), ptr(col_max),
+                     stream_handle())
         n_cells = counts.C
         if comm is not None:
             comm.all_reduce_sum(row_sum)
@@ -202,7 +205,16 @@ class ResidualOperator:
         bad = torch.stack([(col_sum == 0).any(), (row_sum == 0).any()]).to(torch.int64)
         if comm is not None:
             comm.all_reduce_max(bad)
-        head = torch.cat([row_sum.sum().reshape(1), bad]).cpu().numpy()
+        # Can a residual reach the upper clip sqrt(C)?  z = (x - mu) / sqrt(mu (1 + mu/theta)) < x / sqrt(mu), and
+        # mu = r_c s_g / T >= r_min s_g / T, so gene g cannot if  x_max(g) / sqrt(r_min s_g / T) < clip.  When this holds for
+        # every gene (typical: a count that large needs an outlier cell), the pass kernels skip the per-entry clip test;
+        # the result is the same, proved rather than assumed.  One extra G-vector reduction, no extra synchronisation.
+        clip = float(np.float32(np.sqrt(n_cells)))
+        total_d = row_sum.sum().to(torch.float64)
+        mu_min = row_sum.min().to(torch.float64) * col_sum.to(torch.float64) / total_d
+        worst = (col_max.to(torch.float64) / torch.sqrt(mu_min)).nan_to_num(nan=float("inf")).max()
+        may_clip = (worst >= 0.999 * clip).to(torch.int64).reshape(1)
+        head = torch.cat([row_sum.sum().reshape(1), bad, may_clip]).cpu().numpy()
         total = float(head[0])
         if total <= 0:
             raise ValueError("count matrix is empty")
@@ -211,11 +223,12 @@ class ResidualOperator:
             raise ValueError("Input contains all-zero genes or cells: Pearson residuals would be NaN. "
                              "Filter them first (the reference's loader uses min_cells=3).")
         return cls(counts, row_sum, col_sum, row_sum.to(torch.float32), col_sum.to(torch.float32),
-                   total, float(theta), float(np.float32(np.sqrt(n_cells))))
+                   total, float(theta), clip, upper_clip_inactive=not bool(head[3]))
 
     def struct(self, row_shift=None, col_shift=None) -> ResidualMatrix:
         return ResidualMatrix(ptr(self.counts.data), self.C, self.G, self.counts.ld, ptr(self.row_sum_f),
-                              ptr(self.col_sum_f), self.total, self.theta, self.clip, ptr(row_shift), ptr(col_shift))
+                              ptr(self.col_sum_f), self.total, self.theta, self.clip, ptr(row_shift), ptr(col_shift),
+                              1 if self.upper_clip_inactive else 0)
 
     def _scratch_buf(self) -> torch.Tensor:
         need = lib().rsvd_scratch_bytes(self.C, self.G)

@@ -21,7 +21,7 @@ class ResidualMatrix(C.Structure):
     """`gc_residual_matrix` (include/geneclust_b200.h)."""
     _fields_ = [("counts", _p), ("C", _i64), ("G", _i64), ("ld", _i64),
                 ("row_sum_f", _p), ("col_sum_f", _p), ("total", _f32), ("theta", _f32), ("clip", _f32),
-                ("row_shift", _p), ("col_shift", _p)]
+                ("row_shift", _p), ("col_shift", _p), ("upper_clip_inactive", _i32)]
 
 
 # name -> (restype, argtypes).  Must list every function declared in include/geneclust_b200.h
@@ -35,7 +35,7 @@ SIGNATURES = {
     "gc_fp64_probe": (C.c_int, [C.POINTER(C.c_double), _p, _p]),
     "gc_csr_to_counts": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _i64, C.c_int, _p, _p]),
     "gc_dense_to_counts": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _i64, _p, _p]),
-    "gc_count_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
+    "gc_count_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "gc_pearson_residuals": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _f32, _f32, _f32, _p, _i64, _p]),
     "gc_residual_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _f32, _f32, _f32, _p, _p, _p]),
     "gc_rsvd_scratch_bytes": (_i64, [_i64, _i64]),

@@ -65,13 +65,15 @@ __global__ void dense_to_counts_kernel(const float *__restrict__ src, int64_t ld
 constexpr int kSumRows = 128;
 __global__ void __launch_bounds__(256)
 count_sums_kernel(const uint16_t *__restrict__ counts, int64_t C, int64_t G, int64_t ld,
-                  unsigned long long *__restrict__ row_sum, unsigned long long *__restrict__ col_sum) {
+                  unsigned long long *__restrict__ row_sum, unsigned long long *__restrict__ col_sum,
+                  uint32_t *__restrict__ col_max) {
     __shared__ unsigned int srow[kSumRows];
     const int64_t r0 = (int64_t)blockIdx.y * kSumRows;
     const int64_t g0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
     if (threadIdx.x < kSumRows) srow[threadIdx.x] = 0;
     __syncthreads();
     unsigned int cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int mx01 = 0, mx23 = 0, mx45 = 0, mx67 = 0;       // per-gene maxima, two uint16 lanes per word (__vmaxu2)
     const bool active = g0 < ld;  // ld is a multiple of 8, padded columns hold zeros
     const int rows = (int)min((int64_t)kSumRows, C - r0);
     for (int r = 0; r < rows; ++r) {
@@ -79,6 +81,7 @@ count_sums_kernel(const uint16_t *__restrict__ counts, int64_t C, int64_t G, int
         if (active) {
             const uint4 v = *reinterpret_cast<const uint4 *>(counts + (r0 + r) * ld + g0);
             const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+            mx01 = __vmaxu2(mx01, v.x); mx23 = __vmaxu2(mx23, v.y); mx45 = __vmaxu2(mx45, v.z); mx67 = __vmaxu2(mx67, v.w);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned int lo = w[k] & 0xffffu, hi = w[k] >> 16;
@@ -92,9 +95,14 @@ count_sums_kernel(const uint16_t *__restrict__ counts, int64_t C, int64_t G, int
     __syncthreads();
     if (threadIdx.x < rows && srow[threadIdx.x]) atomicAdd(&row_sum[r0 + threadIdx.x], (unsigned long long)srow[threadIdx.x]);
     if (active) {
+        const unsigned int mx[8] = {mx01 & 0xffffu, mx01 >> 16, mx23 & 0xffffu, mx23 >> 16,
+                                    mx45 & 0xffffu, mx45 >> 16, mx67 & 0xffffu, mx67 >> 16};
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (g0 + k < G && cs[k]) atomicAdd(&col_sum[g0 + k], (unsigned long long)cs[k]);
+            if (g0 + k < G && cs[k]) {
+                atomicAdd(&col_sum[g0 + k], (unsigned long long)cs[k]);
+                if (col_max) atomicMax(&col_max[g0 + k], mx[k]);
+            }
     }
 }
 
@@ -510,11 +518,11 @@ static int check_counts_layout(const uint16_t *counts, int64_t C, int64_t G, int
 }
 
 extern "C" int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, unsigned long long *row_sum,
-                             unsigned long long *col_sum, void *stream) {
+                             unsigned long long *col_sum, uint32_t *col_max, void *stream) {
     if (int rc = check_counts_layout(counts, C, G, ld)) return rc;
     GC_REQUIRE(row_sum && col_sum, "null pointer");
     dim3 grid((unsigned)ceil_div<int64_t>(ld, 2048), (unsigned)ceil_div<int64_t>(C, kSumRows));
-    count_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(counts, C, G, ld, row_sum, col_sum);
+    count_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(counts, C, G, ld, row_sum, col_sum, col_max);
     return check_launch("count_sums_kernel");
 }
 

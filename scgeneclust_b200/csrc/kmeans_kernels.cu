@@ -3,6 +3,8 @@
 // Compiled with -fmad=false; where sklearn's order of float32 operations is known it is reproduced.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gc {
 
 constexpr int kDMax = 64;        // feature dimension bound (GeneClust uses 50 PCs)
@@ -314,11 +316,12 @@ __device__ __forceinline__ float chain_sum(const float *q, int len, float acc) {
     for (; i < len; ++i) acc = acc + q[i];
     return acc;
 }
-__global__ void __launch_bounds__(kKppThreads)
-kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
-                 const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
-                 float *closest, float *trial_dist, double *partial, const double *__restrict__ uniforms, int n_trials,
-                 int32_t *__restrict__ indices_out, int round, int last_round, unsigned int *ticket) {
+// Returns (to every thread of the CTA) whether this CTA ran the tail of the round.
+__device__ __forceinline__ bool
+kpp_round_step(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
+               const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
+               float *closest, float *trial_dist, double *partial, const double *__restrict__ uniforms, int n_trials,
+               int32_t *__restrict__ indices_out, int round, int last_round, unsigned int *ticket) {
     __shared__ float sc[kDMax];
     __shared__ double sxx;
     __shared__ double red[kKppThreads];
@@ -332,7 +335,9 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
     __shared__ int64_t s_found[32];
     const int c = blockIdx.y;
     {
-        const float *xc = X + (int64_t)cand[c] * ldx;
+        // cand[] and closest[] were written by the tail CTA of the previous round - in the persistent launch that is
+        // another CTA of the SAME kernel, so they are read through L2 (ld.cg), never from a stale L1 line
+        const float *xc = X + (int64_t)__ldcg(cand + c) * ldx;
         if (threadIdx.x < d) sc[threadIdx.x] = xc[threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -344,7 +349,7 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
         const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         double v = 0.0;
         if (i < n) {
-            const float dd = fminf(closest[i], sqdist_prepared(sc, sxx, Xt, yy, n, i, d));
+            const float dd = fminf(__ldcg(closest + i), sqdist_prepared(sc, sxx, Xt, yy, n, i, d));
             trial_dist[(int64_t)c * n + i] = dd;
             v = (double)dd;
         }
@@ -365,7 +370,7 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
         if (s_is_last) *ticket = 0;              // re-arm for the next launch (stream ordered)
     }
     __syncthreads();
-    if (!s_is_last) return;
+    if (!s_is_last) return false;
     __threadfence();
     const int n_blocks = gridDim.x;
     // choose: potentials in a fixed order, first argmin
@@ -388,11 +393,11 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
         st->best = best;
         s_best = best;
         s_pot = best_pot;
-        indices_out[round] = cand[best];          // centre chosen in this round
+        indices_out[round] = __ldcg(cand + best);     // centre chosen in this round
         carry = 0.f;
     }
     __syncthreads();
-    if (last_round) return;
+    if (last_round) return true;
     // pick for round + 1: closest <- trial_dist[best]; cumsum; searchsorted
     const float *src = trial_dist + (int64_t)s_best * n;
     if (threadIdx.x < n_trials) {
@@ -527,6 +532,47 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
         int64_t f = s_found[threadIdx.x];
         if (f < 0 || f > n - 1) f = n - 1;           // np.clip(candidate_ids, None, n - 1)
         cand[threadIdx.x] = (int32_t)f;
+    }
+    return true;
+}
+
+// one launch per round (fallback when the grid cannot be co-resident)
+__global__ void __launch_bounds__(kKppThreads)
+kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
+                 const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
+                 float *closest, float *trial_dist, double *partial, const double *__restrict__ uniforms, int n_trials,
+                 int32_t *__restrict__ indices_out, int round, int last_round, unsigned int *ticket) {
+    kpp_round_step(st, X, ldx, Xt, yy, n, d, cand, closest, trial_dist, partial, uniforms, n_trials, indices_out, round,
+                   last_round, ticket);
+}
+
+// ALL greedy rounds in one cooperative launch (every CTA is resident, so CTAs may wait for one another): per round the
+// CTA that finishes its distance tile last runs the sequential tail and then publishes the round number; the other CTAs
+// wait for it.  Saves the 198 launches and their inter-kernel gaps (~4 us each of the 23 us a round took).
+__global__ void __launch_bounds__(kKppThreads)
+kpp_persistent_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
+                      const double *__restrict__ yy, int64_t n, int d, int32_t *cand, float *closest, float *trial_dist,
+                      double *partial, const double *__restrict__ uniforms, int n_trials,
+                      int32_t *__restrict__ indices_out, int K, unsigned int *ticket, int *round_flag) {
+    for (int round = 1; round < K; ++round) {
+        const bool ran_tail = kpp_round_step(st, X, ldx, Xt, yy, n, d, cand, closest, trial_dist, partial, uniforms, n_trials,
+                                             indices_out, round, round == K - 1 ? 1 : 0, ticket);
+        if (round == K - 1) break;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (ran_tail) {
+                __threadfence();                                  // the tail's global writes before the flag
+                atomicExch(round_flag, round);
+            } else {
+                unsigned int spins = 0;
+                while (atomicAdd(round_flag, 0) < round) {        // L2 read; the tail takes a few microseconds
+                    __nanosleep(200);
+                    if (++spins > (1u << 24)) __trap();
+                }
+                __threadfence();
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -787,10 +833,28 @@ extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, i
         kpp_pick_kernel<<<1, 1024, 0, st>>>(state, closest, trial, n, uniforms, n_trials, cand, cumsum, indices_out, 1);
         if (int rc = check_launch("kpp_pick_kernel")) return rc;
         dim3 grid((unsigned)n_blocks, (unsigned)n_trials);
-        for (int round = 1; round < K; ++round) {
-            kpp_round_kernel<<<grid, kKppThreads, 0, st>>>(state, X, ldx, Xt, yy, n, d, cand, closest, trial, partial, uniforms,
-                                                           n_trials, indices_out, round, round == K - 1 ? 1 : 0, ticket);
-            if (int rc = check_launch("kpp_round_kernel")) return rc;
+        int per_sm = 0, coop = 0, dev = 0;
+        GC_CUDA(cudaGetDevice(&dev));
+        GC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        GC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kpp_persistent_kernel, kKppThreads, 0));
+        static const bool no_persistent = getenv("GC_KPP_PER_ROUND") != nullptr;       // A/B switch for the tests
+        if (coop && !no_persistent && (int64_t)per_sm * kNumSMs >= (int64_t)n_blocks * n_trials && K > 2) {
+            int *round_flag = (int *)(ticket + 16);
+            GC_CUDA(cudaMemsetAsync(round_flag, 0, sizeof(int), st));
+            int last_dummy = 0;
+            (void)last_dummy;
+            void *args[] = {(void *)&state, (void *)&X, (void *)&ldx, (void *)&Xt, (void *)&yy, (void *)&n, (void *)&d,
+                            (void *)&cand, (void *)&closest, (void *)&trial, (void *)&partial, (void *)&uniforms,
+                            (void *)&n_trials, (void *)&indices_out, (void *)&K, (void *)&ticket, (void *)&round_flag};
+            GC_CUDA(cudaLaunchCooperativeKernel((const void *)kpp_persistent_kernel, grid, dim3(kKppThreads), args, 0, st));
+            if (int rc = check_launch("kpp_persistent_kernel")) return rc;
+        } else {
+            for (int round = 1; round < K; ++round) {
+                kpp_round_kernel<<<grid, kKppThreads, 0, st>>>(state, X, ldx, Xt, yy, n, d, cand, closest, trial, partial,
+                                                               uniforms, n_trials, indices_out, round, round == K - 1 ? 1 : 0,
+                                                               ticket);
+                if (int rc = check_launch("kpp_round_kernel")) return rc;
+            }
         }
     }
     gather_rows_kernel<<<K, kDMax, 0, st>>>(X, ldx, indices_out, K, d, centers_out);

@@ -691,9 +691,14 @@ static int rsvd_apply_impl(const gc_residual_matrix *M, int trans, const float *
         GC_REQUIRE(M->ld < (1ll << 31), "leading dimension too large for the tensor map coordinates");
         CUtensorMap map;
         if (int rcm = make_counts_tensor_map(&map, M->counts, M->C, M->ld, trans)) return rcm;
+        // clip mode: 2 = both bounds, 1 = upper only (lower unreachable when clip >= sqrt(theta)), 0 = none (upper proved
+        // inactive by the caller from the per-gene count maxima)
+        const int clip_mode = lo_clip ? 2 : (M->upper_clip_inactive ? 0 : 1);
         prof_begin(kProfRsvdPass, st);
-        if (trans == 0) rc = lo_clip ? ts_launch<0, true>(map, a, grid, st) : ts_launch<0, false>(map, a, grid, st);
-        else rc = lo_clip ? ts_launch<1, true>(map, a, grid, st) : ts_launch<1, false>(map, a, grid, st);
+        if (trans == 0) rc = clip_mode == 2 ? ts_launch<0, 2>(map, a, grid, st)
+                           : clip_mode == 1 ? ts_launch<0, 1>(map, a, grid, st) : ts_launch<0, 0>(map, a, grid, st);
+        else rc = clip_mode == 2 ? ts_launch<1, 2>(map, a, grid, st)
+                : clip_mode == 1 ? ts_launch<1, 1>(map, a, grid, st) : ts_launch<1, 0>(map, a, grid, st);
         prof_end(kProfRsvdPass, st);
     }
     if (rc) return rc;

@@ -37,8 +37,11 @@ namespace gc {
 #ifndef TS_A_STAGES_N
 #define TS_A_STAGES_N 5
 #endif
+#ifndef TS_WAIT_SLEEP_NS_N
+#define TS_WAIT_SLEEP_NS_N 0
+#endif
 #ifndef TS_I2F_WORDS_N      // of the 4 count words (8 entries) of a chunk, how many are converted by I2F.U16 (XU pipe)
-#define TS_I2F_WORDS_N 2
+#define TS_I2F_WORDS_N 1
 #endif
 constexpr int TS_I2F_WORDS = TS_I2F_WORDS_N;
 constexpr int TS_GROUPS = TS_GROUPS_N;                           // producer groups of four warps
@@ -65,6 +68,14 @@ static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared-memory budget");
 // try_wait / nanosleep / branch loop (the kernel is instruction-issue bound: polling loops of the waiting warps were 15 %
 // of all issued instructions).  Bounded: a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) {
+#if TS_WAIT_SLEEP_NS_N > 0      // developer knob: plain try_wait + fixed nanosleep between polls
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        __nanosleep(TS_WAIT_SLEEP_NS_N);
+        if (spin > (1u << 22)) __trap();
+    }
+    return;
+#endif
     uint32_t ok;
     for (uint32_t spin = 0;; ++spin) {
         asm volatile(
@@ -170,12 +181,14 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 }
 
 // residual of one entry: xf = the count as float, mu = r t
-template <bool LO_CLIP>
+// CLIP: 0 = no test at all (the caller proved that no residual reaches +clip, gc_residual_matrix::upper_clip_inactive, and
+// clip >= sqrt(theta) makes the lower bound unreachable), 1 = upper test only, 2 = both
+template <int CLIP>
 __device__ __forceinline__ float resid1(float xf, float mu, float inv_theta, float clip) {
     const float var = mu * fmaf(mu, inv_theta, 1.0f);
     float v = (xf - mu) * rsqrt_approx(var);
-    v = fminf(v, clip);
-    if (LO_CLIP) v = fmaxf(v, -clip);
+    if (CLIP >= 1) v = fminf(v, clip);
+    if (CLIP >= 2) v = fmaxf(v, -clip);
     return v;
 }
 // two residuals -> one packed bf16 hi word (truncation) and one packed bf16 lo word (rounded remainder); the entry with
@@ -189,7 +202,7 @@ __device__ __forceinline__ void split_pair(float z0, float z1, uint32_t &h, uint
     l = *reinterpret_cast<const uint32_t *>(&lp);
 }
 
-template <int TRANS, bool LO_CLIP>
+template <int TRANS, int CLIP>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -288,8 +301,8 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                                 x0 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7410)) - 8388608.0f;
                                 x1 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7432)) - 8388608.0f;
                             }
-                            z[2 * p] = resid1<LO_CLIP>(x0, fixed * kc[2 * p], a.inv_theta, a.clip);
-                            z[2 * p + 1] = resid1<LO_CLIP>(x1, fixed * kc[2 * p + 1], a.inv_theta, a.clip);
+                            z[2 * p] = resid1<CLIP>(x0, fixed * kc[2 * p], a.inv_theta, a.clip);
+                            z[2 * p + 1] = resid1<CLIP>(x1, fixed * kc[2 * p + 1], a.inv_theta, a.clip);
                         }
                     } else {
 #pragma unroll
@@ -297,7 +310,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                             const uint32_t v = lds_u16(raw_row + (uint32_t)(c * 8 + e) * 256u);
                             const float xf = e < 2 * TS_I2F_WORDS ? (float)(unsigned short)v
                                                                   : __uint_as_float(v | a.magic) - 8388608.0f;
-                            z[e] = resid1<LO_CLIP>(xf, fixed * kc[e], a.inv_theta, a.clip);
+                            z[e] = resid1<CLIP>(xf, fixed * kc[e], a.inv_theta, a.clip);
                         }
                     }
 #pragma unroll
@@ -443,16 +456,16 @@ static int make_counts_tensor_map(CUtensorMap *map, const uint16_t *counts, int6
     return 0;
 }
 
-template <int TRANS, bool LO_CLIP>
+template <int TRANS, int CLIP>
 static int ts_launch(const CUtensorMap &map, const TcArgs &a, dim3 grid, cudaStream_t st) {
     static thread_local bool configured[kMaxDevices] = {};
     const int dev = current_device();
     if (!configured[dev]) {
-        GC_CUDA(cudaFuncSetAttribute(rsvd_apply_ts_kernel<TRANS, LO_CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GC_CUDA(cudaFuncSetAttribute(rsvd_apply_ts_kernel<TRANS, CLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TS_SMEM_BYTES));
         configured[dev] = true;
     }
-    rsvd_apply_ts_kernel<TRANS, LO_CLIP><<<grid, TS_THREADS, TS_SMEM_BYTES, st>>>(map, a);
+    rsvd_apply_ts_kernel<TRANS, CLIP><<<grid, TS_THREADS, TS_SMEM_BYTES, st>>>(map, a);
     return 0;
 }
 

@@ -212,3 +212,37 @@ def test_small_input_pca_solvers_vs_sklearn(torch_cuda, cells, genes, expect):
     rel = np.linalg.norm(got - ref, axis=0) / np.linalg.norm(ref, axis=0)
     print(f"{expect}: {X.shape}, max per-component rel err {rel.max():.2e}")
     assert got.shape == ref.shape and rel.max() <= 1e-3
+
+
+def test_upper_clip_is_skipped_only_when_proved_inactive(torch_cuda, small_counts):
+    """The pass kernels drop the per-entry `min(z, sqrt(C))` only when `ResidualOperator.from_counts` has PROVED from the
+    per-gene count maxima that no residual can reach it.  A matrix with one outlier count in a rare gene does reach the
+    clip: the proof must fail and the product must match the oracle's clipped residuals; the unmodified matrix passes
+    the proof and gives the same product as the always-clipping kernels."""
+    torch = torch_cuda
+    from oracle import stages
+    from scgeneclust_b200._device import ResidualOperator, ingest_counts
+    _, X, _ = small_counts
+    X = np.ascontiguousarray(X[:900, :1200])
+    X = X[:, X.sum(0) > 0].copy()
+    op = ResidualOperator.from_counts(ingest_counts(X))
+    assert op.upper_clip_inactive
+    rs = np.random.RandomState(3)
+    Q = np.zeros((X.shape[1], 64), np.float32)
+    Q[:, :60] = rs.standard_normal((X.shape[1], 60))
+    Qd = torch.from_numpy(Q).cuda()
+    y_ts = op.apply(0, Qd).cpu().numpy()
+    y_simt = op.apply(0, Qd, kernel='simt').cpu().numpy()
+    assert np.abs(y_ts - y_simt).max() <= 2e-4 * np.abs(y_simt).max()
+    # an outlier: 400 counts of the rarest gene in one cell -> residual far above sqrt(900) = 30
+    g = int(np.argmin(X.sum(0)))
+    Xo = X.copy()
+    Xo[17, g] = 400
+    Zo = stages.pearson_residuals(Xo.astype(np.float32))
+    assert Zo[17, g] == np.float32(np.sqrt(Xo.shape[0]))               # the oracle clipped it
+    opo = ResidualOperator.from_counts(ingest_counts(Xo))
+    assert not opo.upper_clip_inactive
+    for trans, panel in ((0, Q), (1, np.pad(rs.standard_normal((Xo.shape[0], 60)).astype(np.float32), ((0, 0), (0, 4))))):
+        ref = (Zo.astype(np.float64) @ panel) if trans == 0 else (Zo.astype(np.float64).T @ panel)
+        got = opo.apply(trans, torch.from_numpy(np.ascontiguousarray(panel)).cuda()).cpu().numpy()
+        assert np.abs(got[:, :60] - ref[:, :60]).max() <= 2e-4 * np.abs(ref).max()
