@@ -190,6 +190,11 @@ int gc_paired_dist(const float *X, int64_t ldx, int64_t n, int d, const float *c
  * scale = 1 / range (range < 10 eps -> 1) (scGeneClust/tl/cluster.py:102-104).  scratch: 2*K int32. */
 int gc_closeness(const float *dist, const int32_t *labels, int64_t n, int K, int32_t *scratch, float *closeness,
                  void *stream);
+/* Per-cluster size and the FIRST index of the maximum / minimum of a non-negative float32 value (the closeness): what the
+ * pandas groupby(...).nlargest(1) / .nsmallest(1) of scGeneClust/tl/selection.py:57-59 pick.  labels in [0, K).
+ * out: 3 K int32 = counts | first arg-max | first arg-min (0x7fffffff for an empty cluster); scratch: 2 K int32. */
+int gc_cluster_extremes(const float *value, const int32_t *labels, int64_t n, int K, int32_t *out, int32_t *scratch,
+                        void *stream);
 
 /* a5  Binomial deviance of the singleton-cluster genes (post-hoc filtering): compute_deviance of
  * scGeneClust/tl/selection.py:82-89 on the float32 residual columns X (C x m, row-major, contiguous), with numpy's

@@ -518,7 +518,10 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     # It is never all-reduced and normalised redundantly: reduce-scatter hands every rank one row chunk of the sum, the
     # Cholesky-QR runs on that chunk (64 x 64 Gram all-reduced), and the normalised chunks are all-gathered - the same
     # NVLink bytes as the all-reduce, 1/world of the panel algebra per rank.
-    sliced = comm is not None and comm.world > 1
+    # GC_PANEL_EXCHANGE=allreduce keeps the previous scheme (all-reduce + replicated normalisation) for A/B timing
+    import os as _os
+    sliced = comm is not None and comm.world > 1 and _os.environ.get("GC_PANEL_EXCHANGE", "rs_ag") != "allreduce"
+    replicated_ar = comm is not None and comm.world > 1 and not sliced
     if sliced:
         chunk = comm.row_chunk(op.C)
         c_pad = chunk * comm.world
@@ -538,6 +541,8 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         """Raw pass.  Gene-sharded trans = 0 output is this rank's PARTIAL sum (in tmp_c): `normalise` reduces it."""
         out = tmp_c if trans == 0 else tmp_g
         op.apply(trans, Qin, row_shift, col_shift, out=out, simt=simt)
+        if replicated_ar and trans == 0:
+            comm.all_reduce_sum(out)
         return out
 
     def chol_qr_chunk(cur, n_steps=1):
@@ -563,7 +568,10 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
         cur, dst = Y, (buf_c if trans == 0 else buf_g)
         for step in range(n_steps):
             out = dst if step % 2 == 0 else Y                  # ping-pong: the second round writes back into Y's buffer
-            alg.chol_qr(cur, q, out, comm if trans == 1 else None, replicated=False)
+            if trans == 0 and replicated_ar:
+                alg.chol_qr(cur, q, out, comm, replicated=True)     # every rank: Gram of its row slice, all-reduced
+            else:
+                alg.chol_qr(cur, q, out, comm if trans == 1 else None, replicated=False)
             cur = out
         return cur
 
@@ -575,6 +583,8 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
             Qp[:, Q_LD - 1] = 1.0
             Y = apply(fwd, Qp)
             colsum = Qp.sum(dim=0, dtype=torch.float64).to(torch.float32)
+            if replicated_ar and fwd == 0:
+                comm.all_reduce_sum(colsum)                    # (Y itself was all-reduced by apply)
             if sliced and fwd == 0:
                 comm.all_reduce_sum(colsum)                    # Omega's rows are sharded like the genes
                 comm.reduce_scatter_rows(tmp_c_pad, sl_in)
@@ -604,6 +614,7 @@ def randomized_pca(op: ResidualOperator, samples: str, random_state: int = 0, n_
     # thin SVD of B through the q x q eigenproblem  B B^T = Uhat S^2 Uhat^T  (float64, on the device)
     if sliced and bwd == 0:
         comm.all_reduce_sum(Bt)                          # cell-space B^T (sklearn did not transpose): needed in full
+    # (replicated_ar: apply() already all-reduced it)
     alg.gram_of(Bt, comm, replicated=(bwd == 0))
     evals = torch.empty(Q_LD, dtype=torch.float64, device=dev)
     uhat = torch.empty((Q_LD, Q_LD), dtype=torch.float32, device=dev)

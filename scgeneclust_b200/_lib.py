@@ -61,6 +61,7 @@ SIGNATURES = {
     "gc_kmeans_minibatch_step": (C.c_int, [_p, _i64, _i64, C.c_int, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gc_kmeans_reassign": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, C.c_int, _f32, _p, _p, _p]),
     "gc_paired_dist": (C.c_int, [_p, _i64, _i64, C.c_int, _p, _p, _p, _p]),
+    "gc_cluster_extremes": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gc_closeness": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gc_binomial_deviance_scratch_bytes": (_i64, [_i64, C.c_int]),
     "gc_binomial_deviance": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p]),

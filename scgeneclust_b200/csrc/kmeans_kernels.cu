@@ -638,6 +638,32 @@ __global__ void closeness_apply_kernel(const float *__restrict__ dist, const int
     out[s] = 1.0f - v;
 }
 
+// Per-cluster size, first arg-max and first arg-min of a non-negative float32 value (the closeness in [0, 1]): what
+// `groupby('cluster')[col].nlargest(1) / .nsmallest(1)` (keep='first') select in scGeneClust/tl/selection.py:57-59.
+// Non-negative floats order like their bit patterns, so the extremes are integer atomics; the first index attaining an
+// extreme is an atomicMin over the indices that hold it.  out: counts[K] | first_max[K] | first_min[K] (int32).
+__global__ void cluster_extremes_init_kernel(int32_t *out, int32_t *ext, int K) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < K) { out[j] = 0; out[K + j] = 0x7fffffff; out[2 * K + j] = 0x7fffffff; ext[j] = -1; ext[K + j] = 0x7fffffff; }
+}
+__global__ void cluster_extremes_value_kernel(const float *__restrict__ v, const int32_t *__restrict__ labels, int64_t n,
+                                              int K, int32_t *out, int32_t *ext) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int l = labels[s], b = __float_as_int(v[s]);
+    atomicAdd(&out[l], 1);
+    atomicMax(&ext[l], b);
+    atomicMin(&ext[K + l], b);
+}
+__global__ void cluster_extremes_index_kernel(const float *__restrict__ v, const int32_t *__restrict__ labels, int64_t n,
+                                              int K, int32_t *out, const int32_t *__restrict__ ext) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int l = labels[s], b = __float_as_int(v[s]);
+    if (b == ext[l]) atomicMin(&out[K + l], (int32_t)s);
+    if (b == ext[K + l]) atomicMin(&out[2 * K + l], (int32_t)s);
+}
+
 // idx[i] = np.searchsorted(cdf, u[i], side='right') = first index with cdf[index] > u[i] (n if none): the mini-batch
 // sampling of RandomState.choice(n, size, p=p) given its uniform draws (numpy mtrand.pyx)
 __global__ void searchsorted_right_kernel(const double *__restrict__ cdf, int64_t n, const double *__restrict__ u, int m,
@@ -754,6 +780,19 @@ extern "C" int gc_searchsorted_right(const double *cdf, int64_t n, const double 
     GC_REQUIRE(cdf && u && idx && n >= 1 && m >= 1, "bad arguments");
     searchsorted_right_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, as_stream(stream)>>>(cdf, n, u, m, idx);
     return check_launch("searchsorted_right_kernel");
+}
+
+extern "C" int gc_cluster_extremes(const float *value, const int32_t *labels, int64_t n, int K, int32_t *out,
+                                   int32_t *scratch, void *stream) {
+    GC_REQUIRE(value && labels && out && scratch && n >= 1 && K >= 1 && n < (1ll << 31), "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const unsigned nb = (unsigned)ceil_div<int64_t>(n, 256);
+    cluster_extremes_init_kernel<<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(out, scratch, K);
+    if (int rc = check_launch("cluster_extremes_init_kernel")) return rc;
+    cluster_extremes_value_kernel<<<nb, 256, 0, st>>>(value, labels, n, K, out, scratch);
+    if (int rc = check_launch("cluster_extremes_value_kernel")) return rc;
+    cluster_extremes_index_kernel<<<nb, 256, 0, st>>>(value, labels, n, K, out, scratch);
+    return check_launch("cluster_extremes_index_kernel");
 }
 
 extern "C" int gc_kmeans_minibatch_step(const float *X, int64_t ldx, int64_t n, int d, int K, const double *cdf,

@@ -26,6 +26,7 @@ class HotPathState:
     redundancy: Optional[torch.Tensor] = None    # device copy of varp['redundancy']
     dense_redundancy: bool = True                # False: the entry point does not return varp['redundancy'] -> stream it
     forest: Optional[tuple] = None               # (edges (n, 2) int64, redundancy of each edge) from the streamed stage
+    fast_clusters: Optional[tuple] = None        # (labels int32, closeness float32, K) on the device, GeneClust-fast
     comm: object = None                          # optional GeneShardComm
     omega: object = None                         # OmegaPrefetch started by `start_omega`
     info: dict = field(default_factory=dict)

@@ -200,8 +200,11 @@ def cluster_genes(adata, img: Optional[np.ndarray], version: Literal['fast', 'ps
                                    random_state=random_state)
         labels = km.fit_predict(X)
         closeness = compute_gene_closeness(X, labels, km.cluster_centers_)
-        adata.var['cluster'] = labels.cpu().numpy()
-        adata.var['closeness'] = closeness.cpu().numpy()
+        labels_h, closeness_h = labels.cpu().numpy(), closeness.cpu().numpy()
+        adata.var['cluster'] = labels_h
+        adata.var['closeness'] = closeness_h
+        # the selection stage reduces these on the device as long as the var columns still hold these values
+        st.fast_clusters = (labels, closeness, int(n_gene_clusters), labels_h, closeness_h)
         st.info['kmeans'] = dict(n_steps=km.n_steps_, centers=km.cluster_centers_)
     else:
         from .confidence import find_high_confidence_cells

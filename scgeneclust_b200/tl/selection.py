@@ -236,6 +236,33 @@ def _first_extreme_per_cluster(cluster: np.ndarray, value: np.ndarray, largest: 
     return first_max if largest else first_min
 
 
+def _select_fast_device(adata, fc, cluster, var_names, post_hoc_filtering, random_state) -> np.ndarray:
+    """GeneClust-fast selection (scGeneClust/tl/selection.py:46-60) with the per-cluster reductions on the device
+    (gc_cluster_extremes: cluster sizes, first arg-max / arg-min of the closeness): the host only maps 2 K indices to
+    gene names.  Same output order: max genes by ascending cluster id, min genes, outliers among singleton clusters."""
+    import torch
+    from .._lib import lib, ptr, stream_handle
+    labels, closeness, K = fc
+    out = torch.empty(3 * K, dtype=torch.int32, device=labels.device)
+    scratch = torch.empty(2 * K, dtype=torch.int32, device=labels.device)
+    lib().cluster_extremes(ptr(closeness), ptr(labels), labels.numel(), K, ptr(out), ptr(scratch), stream_handle())
+    o = out.cpu().numpy()
+    counts, first_max, first_min = o[:K], o[K:2 * K], o[2 * K:]
+    multi = counts > 1
+    single_pos = np.sort(first_max[counts == 1])                   # a singleton's only gene (ascending gene order)
+    if post_hoc_filtering and len(single_pos) > 0:
+        is_single = np.zeros(len(cluster), dtype=bool)
+        is_single[single_pos] = True
+        deviances = _singleton_deviances(adata, is_single)
+        is_outlier = _isolation_forest_outliers(deviances, random_state)
+        logger.opt(colors=True).debug(
+            f"Found <yellow>{is_outlier.sum()}</yellow> outlier(s) in <yellow>{len(single_pos)}</yellow> single gene cluster(s).")
+        outlier_genes = var_names[single_pos][is_outlier]
+    else:
+        outlier_genes = np.array([])
+    return np.hstack((var_names[first_max[multi]], var_names[first_min[multi]], outlier_genes))
+
+
 def select_from_clusters(adata, version: Literal['fast', 'ps'], post_hoc_filtering: bool = True,
                          random_state: int = 0) -> np.ndarray:
     """Same contract as the reference: returns the ndarray of selected gene names.
@@ -245,6 +272,11 @@ def select_from_clusters(adata, version: Literal['fast', 'ps'], post_hoc_filteri
     cluster = adata.var['cluster'].to_numpy()
     var_names = np.asarray(adata.var_names)
     if version == 'fast':
+        st = get_state(adata)
+        fc = st.fast_clusters
+        if (fc is not None and fc[0].numel() == len(cluster) and np.array_equal(cluster, fc[3])
+                and np.array_equal(adata.var['closeness'].to_numpy(), fc[4])):    # var columns untouched since clustering
+            return _select_fast_device(adata, fc[:3], cluster, var_names, post_hoc_filtering, random_state)
         ids, counts = np.unique(cluster, return_counts=True)
         is_single = np.isin(cluster, ids[counts == 1])
         if post_hoc_filtering and (n_single := int(is_single.sum())) > 0:

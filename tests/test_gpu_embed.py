@@ -216,28 +216,36 @@ def test_small_input_pca_solvers_vs_sklearn(torch_cuda, cells, genes, expect):
 
 def test_upper_clip_is_skipped_only_when_proved_inactive(torch_cuda, small_counts):
     """The pass kernels drop the per-entry `min(z, sqrt(C))` only when `ResidualOperator.from_counts` has PROVED from the
-    per-gene count maxima that no residual can reach it.  A matrix with one outlier count in a rare gene does reach the
-    clip: the proof must fail and the product must match the oracle's clipped residuals; the unmodified matrix passes
-    the proof and gives the same product as the always-clipping kernels."""
+    per-gene count maxima that no residual can reach it.  Soundness: whenever the flag is set, the oracle's residuals
+    stay below the clip.  A well-expressed matrix passes the proof and gives the same product as the always-clipping
+    kernels; the same matrix with one outlier count in its rarest gene reaches the clip: the proof must fail and the
+    product must match the oracle's clipped residuals."""
     torch = torch_cuda
     from oracle import stages
     from scgeneclust_b200._device import ResidualOperator, ingest_counts
-    _, X, _ = small_counts
-    X = np.ascontiguousarray(X[:900, :1200])
-    X = X[:, X.sum(0) > 0].copy()
+    _, Xs, _ = small_counts
+    Xs = np.ascontiguousarray(Xs[:900, :1200])
+    Xs = Xs[:, Xs.sum(0) > 0].copy()
+    rs = np.random.RandomState(3)
+    Xd = rs.poisson(rs.uniform(2.0, 9.0, size=300), size=(900, 300)).astype(np.uint16)     # every gene well expressed
+    for X in (Xs, Xd):
+        op = ResidualOperator.from_counts(ingest_counts(X))
+        Z = stages.pearson_residuals(X.astype(np.float32))
+        if op.upper_clip_inactive:
+            assert Z.max() < np.float32(np.sqrt(X.shape[0]))
+    X = Xd
     op = ResidualOperator.from_counts(ingest_counts(X))
     assert op.upper_clip_inactive
-    rs = np.random.RandomState(3)
     Q = np.zeros((X.shape[1], 64), np.float32)
     Q[:, :60] = rs.standard_normal((X.shape[1], 60))
     Qd = torch.from_numpy(Q).cuda()
     y_ts = op.apply(0, Qd).cpu().numpy()
     y_simt = op.apply(0, Qd, kernel='simt').cpu().numpy()
     assert np.abs(y_ts - y_simt).max() <= 2e-4 * np.abs(y_simt).max()
-    # an outlier: 400 counts of the rarest gene in one cell -> residual far above sqrt(900) = 30
+    # an outlier: 4000 counts of the rarest gene in one cell -> residual far above sqrt(900) = 30
     g = int(np.argmin(X.sum(0)))
     Xo = X.copy()
-    Xo[17, g] = 400
+    Xo[17, g] = 4000
     Zo = stages.pearson_residuals(Xo.astype(np.float32))
     assert Zo[17, g] == np.float32(np.sqrt(Xo.shape[0]))               # the oracle clipped it
     opo = ResidualOperator.from_counts(ingest_counts(Xo))
