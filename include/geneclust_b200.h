@@ -263,6 +263,15 @@ int gc_mst_boruvka_edges(const double *cond, int64_t p_begin, int64_t n_cond, co
                          const int32_t *extra_v, const double *extra_w, int64_t n_extra, int64_t N, int32_t *out_u,
                          int32_t *out_v, double *out_w, int32_t *n_out, void *scratch, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * f2  High-confidence cells (scGeneClust/tl/confidence.py:58-60, 104-115): the cells x cells co-membership frequency
+ * matrix of R Gaussian-mixture fits.  labels: R x C int32 (mixture component of every cell per fit), probas: R x C
+ * float64 (its maximum posterior).  freq (C x C uint8, row-major): for j > i the number of fits in which
+ * proba_i >= p, proba_j > p and label_i == label_j; zero elsewhere.  scratch: 2 R C int32.  R <= 32.
+ * ------------------------------------------------------------------------------------------------------- */
+int gc_comembership_counts(const int32_t *labels, const double *probas, int64_t C, int R, double p, uint8_t *freq,
+                           int32_t *scratch, void *stream);
+
 /* HOST function (all pointers are host memory, no GPU work): the HDBSCAN tail of GeneClust-ps
  * (scGeneClust/tl/cluster.py:127-130: hdbscan label -> condense_tree(., min_cluster_size) -> compute_stability ->
  * get_clusters('eom', allow_single_cluster=False) labelling).  mst_sorted_host: n_edges x 3 (i, j, weight), ascending by

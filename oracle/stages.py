@@ -186,6 +186,34 @@ def gene_complementarity(Z: np.ndarray, clusters, edges, random_state: int = 0) 
 
 
 # ---------------------------------------------------------------------------------------------------------
+# f2  high-confidence cells: mixture fits + co-membership            scGeneClust/tl/confidence.py:55-60, 82-115
+# ---------------------------------------------------------------------------------------------------------
+def cell_co_membership(labels: np.ndarray, probas: np.ndarray, p: float = 0.95) -> np.ndarray:
+    """confidence.py:110-114 for one mixture fit: co[i, j > i] = (proba_i >= p) and (proba_j > p) and label_i == label_j."""
+    n = labels.shape[0]
+    co = np.zeros((n, n))
+    for i in range(n - 1):
+        if probas[i] >= p:
+            co[i, i + 1:] = np.logical_and(probas[i + 1:] > p, labels[i + 1:] == labels[i])
+    return co
+
+
+def mixture_labels_probas(X_pca: np.ndarray, n_clusters: int, idx: int, random_state: int = 0):
+    """confidence.py:98-104: the reference's GaussianMixture call on the first `idx` cell PCs."""
+    from sklearn.mixture import GaussianMixture
+    X = X_pca[:, :idx]
+    gmm = GaussianMixture(n_components=n_clusters, init_params='k-means++', random_state=random_state).fit(X)
+    return gmm.predict(X), gmm.predict_proba(X).max(1)
+
+
+def co_membership_frequency(X_pca: np.ndarray, n_clusters: int, n_components: int = 10, random_state: int = 0):
+    """confidence.py:55-60: sum of the co-membership matrices of the fits on PC prefixes 2 .. n_components + 1."""
+    mats = [cell_co_membership(*mixture_labels_probas(X_pca, n_clusters, idx, random_state))
+            for idx in range(2, 2 + n_components)]
+    return np.sum(mats, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # whole fast path on the CPU (timed as the cpu_baseline / reference arm)     scGeneClust/_model.py:123-133
 # ---------------------------------------------------------------------------------------------------------
 def geneclust_fast(counts: np.ndarray, var_names, n_var_clusters: int, random_state: int = 0,

@@ -74,6 +74,7 @@ SIGNATURES = {
     "gc_mst_scratch_bytes": (_i64, [_i64]),
     "gc_mst_boruvka": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "gc_mst_boruvka_edges": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "gc_comembership_counts": (C.c_int, [_p, _p, _i64, C.c_int, _f64, _p, _p, _p]),
     "gc_host_hdbscan_tree": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "gc_host_iforest_depths": (C.c_int, [_p, C.c_int, C.c_uint32, C.c_int, _p, _p]),
     "gc_synth_counts": (C.c_int, [_u64, _i64, _i64, _i64, _i64, _p, _p, C.c_int, _p, _p, C.c_int, _p, C.c_int,

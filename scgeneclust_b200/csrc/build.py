@@ -25,6 +25,7 @@ SOURCES = [
     ("rng_kernels.cu", ["-fmad=false"]),
     ("deviance_kernels.cu", ["-fmad=false"]),
     ("mst_kernels.cu", []),
+    ("confidence_kernels.cu", []),
     ("host_tail.cu", []),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

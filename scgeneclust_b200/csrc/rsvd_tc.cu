@@ -28,6 +28,7 @@
 // Bound: HBM (algorithmic 2 B/entry); the producer ALU work (12 lane-instructions per entry) is the practical limiter.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -301,15 +302,21 @@ tc_prep_kernel(const float *__restrict__ Q, int64_t n_k, int64_t n_k_pad, const 
 }
 
 // colsum[0..63] = sum_k Q[k,:], colsum[64..127] = sum_k k_shift[k] Q[k,:]   (fixed order => deterministic):
-// 1024 threads = 128 outputs x 8 lanes; lane l adds blocks l, l+8, ... in order, the 8 lane sums are folded by a
-// fixed shuffle tree
-__global__ void __launch_bounds__(1024) tc_colsum_kernel(const double *__restrict__ part, int n_blocks, float *__restrict__ colsum) {
-    const int e = threadIdx.x >> 3, l = threadIdx.x & 7;
+// one CTA per output value e; thread t adds blocks t, t + 256, ... in order, then a fixed shared-memory tree.  (A single
+// CTA for all 128 values took 0.1 ms per pass at 400 000 rows.)
+__global__ void __launch_bounds__(256) tc_colsum_kernel(const double *__restrict__ part, int n_blocks, float *__restrict__ colsum) {
+    __shared__ double red[256];
+    const int e = blockIdx.x, t = threadIdx.x;
     double s = 0.0;
-    for (int b = l; b < n_blocks; b += 8) s += part[(int64_t)b * 128 + e];
+    for (int b = t; b < n_blocks; b += 256) s += part[(int64_t)b * 128 + e];
+    red[t] = s;
+    __syncthreads();
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
-    if (l == 0) colsum[e] = (float)s;
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
+        __syncthreads();
+    }
+    if (t == 0) colsum[e] = (float)red[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -568,19 +575,28 @@ __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_
 
 // split-K heuristic (one CTA per SM): minimise  waves x (stages per CTA + fixed cost of a CTA), the fixed cost (barrier /
 // TMEM set-up, first loads, epilogue: ~3 us) counted as 4 stages; among choices within 1.5 % the fewest slabs win
-// (less partial traffic).  50 000 x 20 000: 3 slabs for M Q (8 waves), 13 for M^T Q; with the genes sharded 8 ways
-// (400 000 x 2 500 per GPU) M Q runs unsplit instead of doubling the CTA count for 2 % better wave filling.
+// (less partial traffic).
+// ACCURACY bound on the slab length: the tensor core's fp32 accumulate TRUNCATES, so an accumulator that takes n UMMAs
+// ends up ~n x 1.4e-8 too small in magnitude (measured, scripts/pass_accuracy.py: 16 slabs -1.1e-6, 1 slab -2e-5 ... -5e-5
+// at 50 000 x 20 000).  At config c5 the unbounded heuristic gave slabs of 700+ stages and the gene-sharded and
+// single-GPU embeddings of the same matrix differed by 7e-2 in the trailing components.  Slabs are therefore capped at
+// kMaxSlabStages stages (4 UMMAs per accumulator and stage); the slab partials are summed in round-to-nearest fp32 by
+// the reduce kernel.
+constexpr int kMaxSlabStages = 48;
 __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
-    static const int forced = []() { const char *e = getenv("GC_RSVD_SPLIT"); return e ? atoi(e) : 0; }();   // developer knob
+    static const int forced = []() { const char *e = getenv("GC_RSVD_SPLIT"); return e ? atoi(e) : 0; }();   // developer knobs
+    static const int max_stages = []() { const char *e = getenv("GC_RSVD_MAX_STAGES"); return e ? atoi(e) : kMaxSlabStages; }();
     if (forced > 0) return forced;
     const int64_t slots = (int64_t)kNumSMs;
-    int best = 1;
+    const int64_t stages_total = ceil_div<int64_t>(n_k, TC_TK);
+    const int s_min = (int)std::max<int64_t>(1, ceil_div<int64_t>(stages_total, max_stages));
+    int best = s_min;
     int64_t best_cost = 0;
-    for (int s = 1; s <= 64; ++s) {
+    for (int s = s_min; s <= s_min + 64; ++s) {
         const int64_t k_per = ceil_div<int64_t>(ceil_div<int64_t>(n_k, s), TC_TK) * TC_TK;
-        if (s > 1 && k_per < 8 * TC_TK) break;
+        if (s > s_min && k_per < 8 * TC_TK) break;
         const int64_t cost = ceil_div<int64_t>(n_tiles * s, slots) * (k_per / TC_TK + 4);
-        if (s == 1 || cost * 1000 < best_cost * 985) { best_cost = cost; best = s; }
+        if (s == s_min || cost * 1000 < best_cost * 985) { best_cost = cost; best = s; }
     }
     return best;
 }
@@ -670,10 +686,10 @@ static int rsvd_apply_impl(const gc_residual_matrix *M, int trans, const float *
                                                   M->row_sum_f, M->C, ceil128(M->C), M->col_sum_f, M->G, ceil128(M->ld),
                                                   1.0f / M->total, s.rpad, s.tpad);
     if (int rc = check_launch("tc_prep_kernel")) return rc;
-    tc_colsum_kernel<<<1, 1024, 0, st>>>(s.colsum_part, s.prep_blocks, s.colsum);
+    tc_colsum_kernel<<<128, 256, 0, st>>>(s.colsum_part, s.prep_blocks, s.colsum);
     if (int rc = check_launch("tc_colsum_kernel")) return rc;
 
-    GC_REQUIRE(a.n_split <= 65535, "too many k slabs");
+    GC_REQUIRE(a.n_split <= 65535, "too many k slabs");   // (1 M cells / (48 stages x 64) = 326 slabs at config c5)
     GC_REQUIRE(M->C < (1ll << 31), "more than 2^31 cells");
     dim3 grid((unsigned)n_tiles, (unsigned)a.n_split);
     const bool lo_clip = !(M->clip * M->clip >= M->theta);     // z > -sqrt(theta) always: lower clip is dead otherwise

@@ -78,3 +78,15 @@ def test_fast_cluster_and_selection_match_reference(golden_dir):
     assert np.array_equal(sel.astype(str), g["selected_plain"])
     assert np.allclose(stages.compute_deviance(g["Zres"][:, :8]), g["deviance_first8"], rtol=0, atol=0,
                        equal_nan=True)
+
+
+def test_cell_co_membership_matches_reference_golden(golden_dir):
+    """f2: the oracle's co-membership restatement against the reference's own `_compute_cell_co_membership`
+    (tests/golden/make_golden_confidence.py), from the stored mixture labels / posteriors."""
+    import os
+    import numpy as np
+    from oracle import stages
+    g = np.load(os.path.join(golden_dir, "confidence_small.npz"), allow_pickle=False)
+    freq = np.sum([stages.cell_co_membership(lab, pr, float(g["p"])) for lab, pr in zip(g["labels"], g["probas"])], axis=0)
+    assert np.array_equal(freq, g["frequency"].astype(np.float64))
+    assert not np.tril(freq).any()
