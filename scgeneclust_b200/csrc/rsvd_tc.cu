@@ -705,6 +705,8 @@ static int rsvd_apply_impl(const gc_residual_matrix *M, int trans, const float *
         prof_end(kProfRsvdPass, st);
     } else {
         GC_REQUIRE(M->ld < (1ll << 31), "leading dimension too large for the tensor map coordinates");
+        // persistent launch: one CTA per SM walks the (tile, slab) items
+        grid = dim3((unsigned)std::min<int64_t>(n_tiles * a.n_split, (int64_t)kNumSMs), 1);
         CUtensorMap map;
         if (int rcm = make_counts_tensor_map(&map, M->counts, M->C, M->ld, trans)) return rcm;
         // clip mode: 2 = both bounds, 1 = upper only (lower unreachable when clip >= sqrt(theta)), 0 = none (upper proved

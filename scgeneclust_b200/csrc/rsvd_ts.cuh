@@ -47,7 +47,9 @@ constexpr int TS_I2F_WORDS = TS_I2F_WORDS_N;
 constexpr int TS_GROUPS = TS_GROUPS_N;                           // producer groups of four warps
 constexpr int TS_A_STAGES = TS_A_STAGES_N;                       // A-operand slots in tensor memory (64 columns each)
 constexpr int TS_PRODUCER_WARPS = 4 * TS_GROUPS;
-constexpr int TS_THREADS = (TS_PRODUCER_WARPS + 3) * 32;
+constexpr int TS_EPI_WARPS = 4;                                  // one per TMEM lane quarter
+constexpr int TS_MMA_WARP = TS_PRODUCER_WARPS + TS_EPI_WARPS;
+constexpr int TS_THREADS = (TS_PRODUCER_WARPS + TS_EPI_WARPS + 3) * 32;
 constexpr int TS_RAW_STAGES = 9;                                 // raw count tiles in flight (TMA runs this far ahead)
 constexpr int TS_B_STAGES = 4;
 constexpr int TS_RAW_BYTES = TC_TM * TC_TK * 2;                  // 16 KB raw uint16 tile
@@ -56,11 +58,11 @@ constexpr int TS_KC_BYTES = TC_TK * 4;                           // 256 B of per
 constexpr int TS_OFF_PANEL = TS_RAW_STAGES * TS_RAW_BYTES;
 constexpr int TS_OFF_KC = TS_OFF_PANEL + TS_B_STAGES * TS_PANEL_BYTES;
 constexpr int TS_OFF_BAR = TS_OFF_KC + TS_RAW_STAGES * TS_KC_BYTES;
-constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * TS_B_STAGES + 1;
+constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * TS_B_STAGES + 2;
 constexpr int TS_SMEM_BYTES = TS_OFF_BAR + 8 * TS_N_BARS + 16 + 1024 /*align*/;
 constexpr int TS_ACC_COLS = 192, TS_A_COLS = 64;   // D1 = [0, 128): A_hi [Q_hi | Q_lo];  D2 = [128, 192): A_lo Q_hi
 static_assert(TS_ACC_COLS + TS_A_STAGES * TS_A_COLS <= TC_TMEM_COLS, "TMEM budget");
-static_assert(TS_GROUPS >= 4, "the epilogue uses sixteen producer warps");
+static_assert(TS_THREADS <= 1024, "too many warps");
 static_assert(TS_SMEM_BYTES <= 227 * 1024, "shared-memory budget");
 
 // mbarrier wait that lets the HARDWARE park the warp: try_wait with a suspend-time hint returns only when the phase
@@ -202,6 +204,13 @@ __device__ __forceinline__ void split_pair(float z0, float z1, uint32_t &h, uint
     l = *reinterpret_cast<const uint32_t *>(&lp);
 }
 
+// One work item = one 128-row output tile x one k-slab.  The kernel is PERSISTENT: the grid is one CTA per SM and a CTA
+// walks the items  blockIdx.x, blockIdx.x + gridDim.x, ...  with its pipeline (rings, barrier phases, TMEM) running
+// straight through the item boundaries: the producers start the next item's stages while the UMMAs of the last stages
+// and the epilogue of the previous item are still in flight.  Short slabs are what the accumulation accuracy wants
+// (kMaxSlabStages); with one CTA launch per slab their fixed costs (launch, TMEM allocation, pipeline fill and drain,
+// ~4 us) were 7 % of the pass at 48 stages per slab.
+// Item order: item = split * n_tiles + tile, so CTAs that run at the same time read the same panel k-range (L2 hits).
 template <int TRANS, int CLIP>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
@@ -211,17 +220,20 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     const uint32_t bar_raw_full = bar_base, bar_raw_empty = bar_raw_full + 8 * TS_RAW_STAGES;
     const uint32_t bar_a_full = bar_raw_empty + 8 * TS_RAW_STAGES, bar_a_empty = bar_a_full + 8 * TS_A_STAGES;
     const uint32_t bar_b_full = bar_a_empty + 8 * TS_A_STAGES, bar_b_empty = bar_b_full + 8 * TS_B_STAGES;
-    const uint32_t bar_accum = bar_b_empty + 8 * TS_B_STAGES;
+    const uint32_t bar_acc_full = bar_b_empty + 8 * TS_B_STAGES, bar_acc_free = bar_acc_full + 8;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (bar_accum + 8 - smem_base));
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (bar_acc_free + 8 - smem_base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * TC_TM;
-    const int split = blockIdx.y;
-    const int64_t k_lo = split * a.k_per_split, k_hi = min(a.n_k, k_lo + a.k_per_split);
-    const int n_it = (int)ceil_div<int64_t>(max((int64_t)0, k_hi - k_lo), TC_TK);
+    const int64_t n_tiles = ceil_div<int64_t>(a.n_out, TC_TM);
+    const int64_t n_items = n_tiles * a.n_split;
+    // stages of an item: every slab has k_per_split / 64 stages except the last one of the k range
+    auto item_stages = [&](int64_t item) -> int {
+        const int64_t k_lo = (item / n_tiles) * a.k_per_split, k_hi = min(a.n_k, k_lo + a.k_per_split);
+        return (int)ceil_div<int64_t>(max((int64_t)0, k_hi - k_lo), TC_TK);
+    };
 
-    if (warp == TS_PRODUCER_WARPS) {
+    if (warp == TS_MMA_WARP) {
         if (lane == 0) {
             for (int s = 0; s < TS_RAW_STAGES; ++s) {
                 mbar_init(bar_raw_full + 8 * s, 1);            // the copy issuer's arrive.expect_tx
@@ -235,7 +247,8 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 mbar_init(bar_b_full + 8 * s, 1);
                 mbar_init(bar_b_empty + 8 * s, 1);
             }
-            mbar_init(bar_accum, 1);
+            mbar_init(bar_acc_full, 1);                        // tcgen05.commit after the last stage of an item
+            mbar_init(bar_acc_free, TS_EPI_WARPS);             // the epilogue warps have read the accumulators
             fence_mbar_init();
         }
         __syncwarp();
@@ -250,9 +263,6 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         // =============================== producers ===============================
         const int group = warp >> 2, quarter = warp & 3;
         const int m = quarter * 32 + lane;                                        // row of the tile = TMEM lane
-        // the constant of this thread's output row (TRANS 0: r of its cell, TRANS 1: s/T of its gene); the padded vectors
-        // hold 1.0 beyond the matrix, where TMA delivered zero counts: every residual stays finite
-        const float fixed = __ldg((TRANS == 0 ? a.rpad : a.tpad) + m0 + m);
         const uint32_t a_lane = tmem_d + ((uint32_t)(quarter * 32) << 16) + TS_ACC_COLS;
         // TRANS 0: raw tile = 128 cells x 64 genes, 128-byte rows, TMA SWIZZLE_128B: 16-byte chunk c of row m sits at
         //          chunk c ^ (m & 7) - eight consecutive lanes read eight different bank groups.
@@ -262,107 +272,129 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         uint32_t chunk_off[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) chunk_off[c] = row_off + ((((uint32_t)c) ^ (uint32_t)(m & 7)) << 4);
-        for (int it = group; it < n_it; it += TS_GROUPS) {
-            const int rs = it % TS_RAW_STAGES;                    // raw slot of this stage (the TMA runs ahead of the groups)
-            // TMEM A slot of this stage.  There are more slots than groups: the slot was last used by stage it - TS_A_STAGES,
-            // an EARLIER stage than this group's previous one, so its UMMAs have normally retired by now (with one slot per
-            // group every group waited for its own, most recently issued, UMMAs: 32 % of all stall samples)
-            const int as = it % TS_A_STAGES;
-            const uint32_t a_col = a_lane + (uint32_t)as * TS_A_COLS;
-            const uint32_t raw_tile = smem_base + rs * TS_RAW_BYTES;
-            const uint32_t raw_row = raw_tile + row_off;
-            const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
-            mbar_wait_park(bar_raw_full + 8 * rs, (uint32_t)(it / TS_RAW_STAGES) & 1);
+        int64_t g0 = 0;                                            // stages of this CTA's earlier items
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int n_it = item_stages(item);
+            const int64_t m0 = (item % n_tiles) * TC_TM;
+            // the constant of this thread's output row (TRANS 0: r of its cell, TRANS 1: s/T of its gene); the padded
+            // vectors hold 1.0 beyond the matrix, where TMA delivered zero counts: every residual stays finite
+            const float fixed = __ldg((TRANS == 0 ? a.rpad : a.tpad) + m0 + m);
+            // group g takes the stages whose running number gs = g0 + it is congruent to g: the rotation continues
+            // across items, so the four groups stay evenly loaded whatever the slab length
+            for (int it = (int)((group - g0 % TS_GROUPS + TS_GROUPS) % TS_GROUPS); it < n_it; it += TS_GROUPS) {
+                const int64_t gs = g0 + it;
+                const int rs = (int)(gs % TS_RAW_STAGES);         // raw slot of this stage (the TMA runs ahead of the groups)
+                // TMEM A slot of this stage.  There are more slots than groups: the slot was last used by stage
+                // gs - TS_A_STAGES, an EARLIER stage than this group's previous one, so its UMMAs have normally retired
+                const int as = (int)(gs % TS_A_STAGES);
+                const uint32_t a_col = a_lane + (uint32_t)as * TS_A_COLS;
+                const uint32_t raw_tile = smem_base + rs * TS_RAW_BYTES;
+                const uint32_t raw_row = raw_tile + row_off;
+                const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
+                mbar_wait_park(bar_raw_full + 8 * rs, (uint32_t)(gs / TS_RAW_STAGES) & 1);
 #pragma unroll
-            for (int c2 = 0; c2 < TC_TK / 16; ++c2) {             // 16 entries (k = 16 c2 .. 16 c2 + 15) per round
-                uint32_t hi[8], lo[8];
+                for (int c2 = 0; c2 < TC_TK / 16; ++c2) {             // 16 entries (k = 16 c2 .. 16 c2 + 15) per round
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int c = 2 * c2 + half;                  // 16-byte chunk of 8 entries
-                    const uint4 k0 = lds128(kc_s + c * 32), k1 = lds128(kc_s + c * 32 + 16);   // warp-wide broadcast
-                    const float kc[8] = {__uint_as_float(k0.x), __uint_as_float(k0.y), __uint_as_float(k0.z),
-                                         __uint_as_float(k0.w), __uint_as_float(k1.x), __uint_as_float(k1.y),
-                                         __uint_as_float(k1.z), __uint_as_float(k1.w)};
-                    float z[8];
-                    if constexpr (TRANS == 0) {
-                        const uint4 raw = lds128(raw_tile + chunk_off[c]);
-                        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+                    for (int half = 0; half < 2; ++half) {
+                        const int c = 2 * c2 + half;                  // 16-byte chunk of 8 entries
+                        const uint4 k0 = lds128(kc_s + c * 32), k1 = lds128(kc_s + c * 32 + 16);   // warp-wide broadcast
+                        const float kc[8] = {__uint_as_float(k0.x), __uint_as_float(k0.y), __uint_as_float(k0.z),
+                                             __uint_as_float(k0.w), __uint_as_float(k1.x), __uint_as_float(k1.y),
+                                             __uint_as_float(k1.z), __uint_as_float(k1.w)};
+                        float z[8];
+                        if constexpr (TRANS == 0) {
+                            const uint4 raw = lds128(raw_tile + chunk_off[c]);
+                            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            // exact uint16 -> float.  Two ways, mixed to balance the pipes: splice the 16 bits under the
-                            // 2^23 exponent and subtract 2^23 (PRMT on the ALU pipe + FADD: two issue slots), or one
-                            // I2F.U16 with a half-word selector (one issue slot, but on the quarter-rate XU pipe that
-                            // also runs the MUFU.RSQ of every entry)
-                            float x0, x1;
-                            if (p < TS_I2F_WORDS) {
-                                x0 = (float)(unsigned short)(w[p] & 0xffffu);
-                                x1 = (float)(unsigned short)(w[p] >> 16);
-                            } else {
-                                x0 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7410)) - 8388608.0f;
-                                x1 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7432)) - 8388608.0f;
+                            for (int p = 0; p < 4; ++p) {
+                                // exact uint16 -> float.  Two ways, mixed to balance the pipes: splice the 16 bits under
+                                // the 2^23 exponent and subtract 2^23 (PRMT on the ALU pipe + FADD: two issue slots), or one
+                                // I2F.U16 with a half-word selector (one issue slot, but on the quarter-rate XU pipe that
+                                // also runs the MUFU.RSQ of every entry)
+                                float x0, x1;
+                                if (p < TS_I2F_WORDS) {
+                                    x0 = (float)(unsigned short)(w[p] & 0xffffu);
+                                    x1 = (float)(unsigned short)(w[p] >> 16);
+                                } else {
+                                    x0 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7410)) - 8388608.0f;
+                                    x1 = __uint_as_float(__byte_perm(w[p], a.magic, 0x7432)) - 8388608.0f;
+                                }
+                                z[2 * p] = resid1<CLIP>(x0, fixed * kc[2 * p], a.inv_theta, a.clip);
+                                z[2 * p + 1] = resid1<CLIP>(x1, fixed * kc[2 * p + 1], a.inv_theta, a.clip);
                             }
-                            z[2 * p] = resid1<CLIP>(x0, fixed * kc[2 * p], a.inv_theta, a.clip);
-                            z[2 * p + 1] = resid1<CLIP>(x1, fixed * kc[2 * p + 1], a.inv_theta, a.clip);
-                        }
-                    } else {
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const uint32_t v = lds_u16(raw_row + (uint32_t)(c * 8 + e) * 256u);
-                            const float xf = e < 2 * TS_I2F_WORDS ? (float)(unsigned short)v
-                                                                  : __uint_as_float(v | a.magic) - 8388608.0f;
-                            z[e] = resid1<CLIP>(xf, fixed * kc[e], a.inv_theta, a.clip);
+                            for (int e = 0; e < 8; ++e) {
+                                const uint32_t v = lds_u16(raw_row + (uint32_t)(c * 8 + e) * 256u);
+                                const float xf = e < 2 * TS_I2F_WORDS ? (float)(unsigned short)v
+                                                                      : __uint_as_float(v | a.magic) - 8388608.0f;
+                                z[e] = resid1<CLIP>(xf, fixed * kc[e], a.inv_theta, a.clip);
+                            }
                         }
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) split_pair(z[2 * p], z[2 * p + 1], hi[4 * half + p], lo[4 * half + p]);
                     }
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) split_pair(z[2 * p], z[2 * p + 1], hi[4 * half + p], lo[4 * half + p]);
+                    if (c2 == 0) {
+                        mbar_wait_park(bar_a_empty + 8 * as, ((uint32_t)(gs / TS_A_STAGES) & 1) ^ 1);   // passes at once on the first lap
+                        tc_fence_after();
+                    }
+                    tmem_st8(a_col + 8 * c2, hi);                     // 16 bf16 = 8 columns
+                    tmem_st8(a_col + 32 + 8 * c2, lo);
                 }
-                if (c2 == 0) {
-                    // the TMEM slot was last read by the UMMAs of this group's previous stage
-                    mbar_wait_park(bar_a_empty + 8 * as, ((uint32_t)(it / TS_A_STAGES) & 1) ^ 1);   // passes at once on the first lap
-                    tc_fence_after();
-                }
-                tmem_st8(a_col + 8 * c2, hi);                     // 16 bf16 = 8 columns
-                tmem_st8(a_col + 32 + 8 * c2, lo);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_raw_empty + 8 * rs);              // the raw slot may be refilled
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_full + 8 * as);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_raw_empty + 8 * rs);              // the raw slot may be refilled
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a_full + 8 * as);
+            g0 += n_it;
         }
-
-        // =============================== epilogue ===============================
-        if (n_it > 0) {
-            mbar_wait_park(bar_accum, 0);
-            tc_fence_after();
-        }
-        if (warp < 16 && warp < TS_PRODUCER_WARPS) {
-            // warp w reads TMEM lanes 32 (w % 4) .. +31 (= output rows), 16 output columns (w / 4) of both halves
-            const int col_q = warp >> 2;
-            float acc[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    } else if (warp < TS_PRODUCER_WARPS + TS_EPI_WARPS) {
+        // =============================== epilogue warps ===============================
+        // warp q reads TMEM lanes 32 q .. +31 (= output rows) of the three partial accumulators (hi.hi, hi.lo, lo.hi, summed
+        // in that fixed order) and writes the slab's partial result
+        const int quarter = warp - TS_PRODUCER_WARPS;
+        const uint32_t t_lane = tmem_d + ((uint32_t)(quarter * 32) << 16);
+        uint32_t ph = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int n_it = item_stages(item);
+            const int64_t row = (item % n_tiles) * TC_TM + quarter * 32 + lane;
+            const int64_t split = item / n_tiles;
+            float4 *dst = reinterpret_cast<float4 *>(a.partials + (split * a.n_out + row) * TC_TN);
             if (n_it > 0) {
-                const uint32_t t0 = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col_q * 16);
-                // fixed summation order: hi.hi, hi.lo, lo.hi
+                mbar_wait_park(bar_acc_full, ph);
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int cq = 0; cq < 4; ++cq) {
+                float acc[16];
 #pragma unroll
-                for (int part = 0; part < 3; ++part) {
-                    uint32_t v[16];
-                    tmem_ld16(t0 + part * 64, v);
+                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                if (n_it > 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+                    for (int part = 0; part < 3; ++part) {
+                        uint32_t v[16];
+                        tmem_ld16(t_lane + (uint32_t)(part * 64 + cq * 16), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+                    }
+                }
+                if (row < a.n_out) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dst[cq * 4 + j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
                 }
             }
-            const int64_t row = m0 + m;
-            if (row < a.n_out) {
-                float4 *dst = reinterpret_cast<float4 *>(a.partials + ((int64_t)split * a.n_out + row) * TC_TN + col_q * 16);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            if (n_it > 0) {
+                tc_fence_before();                                  // the TMEM reads before the next item's overwrite
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_free);
+                ph ^= 1;
             }
         }
-    } else if (warp == TS_PRODUCER_WARPS) {
+    } else if (warp == TS_MMA_WARP) {
         // =============================== MMA issuer (whole warp, one elected lane issues) =============
         constexpr uint32_t idesc128 = umma_idesc(0, 1, 128), idesc64 = umma_idesc(0, 1, 64);   // A K-major (TMEM), B MN-major
         constexpr uint32_t b_lbo = 8192u, b_sbo = 1024u;          // K step 2048 B: see umma_stage_ts
@@ -371,45 +403,70 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         // warp-uniform copy of the TMEM base (it came out of shared memory through a vector load): everything derived from
         // it can then live in uniform registers
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
-        for (int it = 0; it < n_it; ++it) {
-            const int s = it % TS_A_STAGES, sb = it % TS_B_STAGES;
-            mbar_wait_park(bar_b_full + 8 * sb, (uint32_t)(it / TS_B_STAGES) & 1);
-            mbar_wait_park(bar_a_full + 8 * s, (uint32_t)(it / TS_A_STAGES) & 1);
+        int64_t g0 = 0;
+        uint32_t ph = 0;
+        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int n_it = item_stages(item);
+            if (n_it == 0) continue;
+            mbar_wait_park(bar_acc_free, ph ^ 1);                   // the previous item's accumulators have been read
             tc_fence_after();
-            umma_stage_ts(tmem_u, tmem_u + TS_ACC_COLS + (uint32_t)s * TS_A_COLS,
-                          b_low0 + (uint32_t)sb * (TS_PANEL_BYTES >> 4), b_hiw, idesc128, idesc64, it > 0 ? 1u : 0u,
-                          bar_a_empty + 8 * s, bar_b_empty + 8 * sb);
+            for (int it = 0; it < n_it; ++it) {
+                const int64_t gs = g0 + it;
+                const int s = (int)(gs % TS_A_STAGES), sb = (int)(gs % TS_B_STAGES);
+                mbar_wait_park(bar_b_full + 8 * sb, (uint32_t)(gs / TS_B_STAGES) & 1);
+                mbar_wait_park(bar_a_full + 8 * s, (uint32_t)(gs / TS_A_STAGES) & 1);
+                tc_fence_after();
+                umma_stage_ts(tmem_u, tmem_u + TS_ACC_COLS + (uint32_t)s * TS_A_COLS,
+                              b_low0 + (uint32_t)sb * (TS_PANEL_BYTES >> 4), b_hiw, idesc128, idesc64, it > 0 ? 1u : 0u,
+                              bar_a_empty + 8 * s, bar_b_empty + 8 * sb);
+            }
+            umma_commit_elect(bar_acc_full);                        // accumulators of this item complete
+            g0 += n_it;
+            ph ^= 1;
         }
-        if (n_it > 0) umma_commit_elect(bar_accum);           // accumulator complete
         __syncwarp();
-    } else if (warp == TS_PRODUCER_WARPS + 1) {
+    } else if (warp == TS_MMA_WARP + 1) {
         // =============================== raw-tile TMA issuer (one thread) ===============================
         if (lane == 0) {
             const uint64_t policy = l2_evict_first_policy();
-            const float *kconst = (TRANS == 0 ? a.tpad : a.rpad) + k_lo;
-            for (int it = 0; it < n_it; ++it) {
-                const int s = it % TS_RAW_STAGES;
-                const int32_t kk = (int32_t)(k_lo + (int64_t)it * TC_TK);
-                mbar_wait_park(bar_raw_empty + 8 * s, ((uint32_t)(it / TS_RAW_STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(bar_raw_full + 8 * s, TS_RAW_BYTES + TS_KC_BYTES);
-                if (TRANS == 0) tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, kk, (int32_t)m0, bar_raw_full + 8 * s, policy);
-                else tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, (int32_t)m0, kk, bar_raw_full + 8 * s, policy);
-                bulk_g2s(smem_base + TS_OFF_KC + s * TS_KC_BYTES, kconst + (int64_t)it * TC_TK, TS_KC_BYTES, bar_raw_full + 8 * s);
+            int64_t g0 = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int n_it = item_stages(item);
+                const int64_t m0 = (item % n_tiles) * TC_TM, k_lo = (item / n_tiles) * a.k_per_split;
+                const float *kconst = (TRANS == 0 ? a.tpad : a.rpad) + k_lo;
+                for (int it = 0; it < n_it; ++it) {
+                    const int64_t gs = g0 + it;
+                    const int s = (int)(gs % TS_RAW_STAGES);
+                    const int32_t kk = (int32_t)(k_lo + (int64_t)it * TC_TK);
+                    mbar_wait_park(bar_raw_empty + 8 * s, ((uint32_t)(gs / TS_RAW_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(bar_raw_full + 8 * s, TS_RAW_BYTES + TS_KC_BYTES);
+                    if (TRANS == 0) tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, kk, (int32_t)m0, bar_raw_full + 8 * s, policy);
+                    else tma_load_2d(smem_base + s * TS_RAW_BYTES, &tmap, (int32_t)m0, kk, bar_raw_full + 8 * s, policy);
+                    bulk_g2s(smem_base + TS_OFF_KC + s * TS_KC_BYTES, kconst + (int64_t)it * TC_TK, TS_KC_BYTES, bar_raw_full + 8 * s);
+                }
+                g0 += n_it;
             }
         }
         __syncwarp();
     } else {
         // =============================== panel-tile copy issuer (one thread) ===============================
         if (lane == 0) {
-            const char *qh = reinterpret_cast<const char *>(a.Qh) + (k_lo / TC_TK) * TC_B_BYTES;
-            const char *ql = reinterpret_cast<const char *>(a.Ql) + (k_lo / TC_TK) * TC_B_BYTES;
-            for (int it = 0; it < n_it; ++it) {
-                const int sb = it % TS_B_STAGES;
-                mbar_wait_park(bar_b_empty + 8 * sb, ((uint32_t)(it / TS_B_STAGES) & 1) ^ 1);
-                const uint32_t b_hi = smem_base + TS_OFF_PANEL + sb * TS_PANEL_BYTES;
-                mbar_arrive_expect_tx(bar_b_full + 8 * sb, TS_PANEL_BYTES);
-                bulk_g2s(b_hi, qh + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);
-                bulk_g2s(b_hi + TC_B_BYTES, ql + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);
+            int64_t g0 = 0;
+            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int n_it = item_stages(item);
+                const int64_t k_lo = (item / n_tiles) * a.k_per_split;
+                const char *qh = reinterpret_cast<const char *>(a.Qh) + (k_lo / TC_TK) * TC_B_BYTES;
+                const char *ql = reinterpret_cast<const char *>(a.Ql) + (k_lo / TC_TK) * TC_B_BYTES;
+                for (int it = 0; it < n_it; ++it) {
+                    const int64_t gs = g0 + it;
+                    const int sb = (int)(gs % TS_B_STAGES);
+                    mbar_wait_park(bar_b_empty + 8 * sb, ((uint32_t)(gs / TS_B_STAGES) & 1) ^ 1);
+                    const uint32_t b_hi = smem_base + TS_OFF_PANEL + sb * TS_PANEL_BYTES;
+                    mbar_arrive_expect_tx(bar_b_full + 8 * sb, TS_PANEL_BYTES);
+                    bulk_g2s(b_hi, qh + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);
+                    bulk_g2s(b_hi + TC_B_BYTES, ql + (int64_t)it * TC_B_BYTES, TC_B_BYTES, bar_b_full + 8 * sb);
+                }
+                g0 += n_it;
             }
         }
         __syncwarp();
@@ -417,7 +474,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == TS_PRODUCER_WARPS) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+    if (warp == TS_MMA_WARP) tmem_dealloc(tmem_d, TC_TMEM_COLS);
 }
 
 // ---- host side: the tensor map of the count matrix -------------------------------------------------------------
