@@ -582,7 +582,7 @@ __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_
 // single-GPU embeddings of the same matrix differed by 7e-2 in the trailing components.  Slabs are therefore capped at
 // kMaxSlabStages stages (4 UMMAs per accumulator and stage); the slab partials are summed in round-to-nearest fp32 by
 // the reduce kernel.
-constexpr int kMaxSlabStages = 48;
+constexpr int kMaxSlabStages = 32;
 __host__ int tc_choose_split(int64_t n_tiles, int64_t n_k) {
     static const int forced = []() { const char *e = getenv("GC_RSVD_SPLIT"); return e ? atoi(e) : 0; }();   // developer knobs
     static const int max_stages = []() { const char *e = getenv("GC_RSVD_MAX_STAGES"); return e ? atoi(e) : kMaxSlabStages; }();
