@@ -294,16 +294,12 @@ def fast_stages(AnnDataLite, X, names, n_clusters):
                 closeness=ad.var['closeness'].to_numpy(), selected=sel)
 
 
-def compare_runs(a: dict, b: dict) -> dict:
-    """Parity figures of run `a` against run `b` (BASELINE.md section 3 parity gates)."""
-    from sklearn.metrics import adjusted_rand_score
-    rel = np.linalg.norm(a['X_pca'] - b['X_pca'], axis=0) / np.linalg.norm(b['X_pca'], axis=0)
-    return {"pca_rel_err_max": float(rel.max()), "pca_rel_err_first10": float(rel[:10].max()),
-            "labels_equal": bool(np.array_equal(a['labels'], b['labels'])),
-            "ari": float(adjusted_rand_score(a['labels'], b['labels'])),
-            "selected_equal": bool(np.array_equal(a['selected'], b['selected'])),
-            "selected_common": int(len(set(a['selected']) & set(b['selected']))),
-            "n_selected": int(len(a['selected'])), "n_selected_other": int(len(b['selected']))}
+def compare_runs(a: dict, b: dict, names, n_clusters: int) -> dict:
+    """Link-wise parity of run `a` (GPU) against run `b` (BASELINE.md section 3 parity gates; oracle.stages.fast_parity):
+    PCA scores to float tolerance, the k-means / closeness / selection tail EXACT against scikit-learn on a's own
+    embedding, and the end-to-end label / list agreement as a reported figure."""
+    from oracle import stages
+    return stages.fast_parity(a, b, names, n_clusters, SEED)
 
 
 def run_native(args, rank: int, world: int, local_rank: int):
@@ -461,7 +457,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
             full = synth.counts(0, cells, 0, G)
             single = fast_stages(AnnDataLite, full, names, args.clusters)
             del full
-            line["sharded_parity"] = dict(compare_runs(sharded, single),
+            line["sharded_parity"] = dict(compare_runs(sharded, single, names, args.clusters),
                                           vs=f"single-GPU run of the same {cells} x {G} matrix on rank 0")
         barrier()
 
@@ -480,7 +476,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
             Xs = twin if world == 1 else osy.synth_counts_c(osy.synth_params(G, SEED), 0, n_sub, 0, G)
             sec, tm, cpu_sub = cpu_fast(Xs, args.clusters)
             line["subsample_check"] = dict(
-                compare_runs(gpu_sub, cpu_sub), cells=n_sub, genes=G, gpus=world, cpu_seconds=sec,
+                compare_runs(gpu_sub, cpu_sub, names, args.clusters), cells=n_sub, genes=G, gpus=world, cpu_seconds=sec,
                 input_identical=bool(same.item()),
                 what=f"GPU ({world} rank(s), genes sharded) vs CPU oracle on cells[0:{n_sub}] of the same counter-based "
                      f"stream; the device-generated block is compared bit for bit with the oracle generator's")
@@ -540,7 +536,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         if n_cells == cells:
             # the same full-size CPU result doubles as a parity check of the benchmarked GPU run
             gpu_res = fast_stages(AnnDataLite, counts, names, args.clusters)
-            line["cpu_parity_full_size"] = compare_runs(gpu_res, cpu_res)
+            line["cpu_parity_full_size"] = compare_runs(gpu_res, cpu_res, names, args.clusters)
         if E is not None:
             workers = max(1, os.cpu_count() - 1)
             pps = cpu_pairs_sample(E.cpu().numpy(), CPU_SAMPLE_PAIRS, workers)

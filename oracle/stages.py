@@ -233,3 +233,40 @@ def geneclust_fast(counts: np.ndarray, var_names, n_var_clusters: int, random_st
         timings.update(normalize=t1 - t0, pca=t2 - t1, kmeans=t3 - t2, select=t4 - t3, total=t4 - t0,
                        kmeans_steps=int(n_steps))
     return dict(Z=Z, X_pca=X_pca, labels=labels, centers=centers, closeness=closeness, selected=selected)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# link-wise parity of a GeneClust-fast run (what the tests / smoke / bench assert; see tests/test_gpu_subsample.py)
+# ---------------------------------------------------------------------------------------------------------
+def fast_parity(gpu: dict, ref: dict, var_names, n_var_clusters: int, random_state: int = 0, Z=None) -> dict:
+    """`gpu` / `ref`: dicts with X_pca, labels, closeness, selected (ref = this module's `geneclust_fast` result or a
+    fixture of it).  Returns
+      pca_rel_err_max / _first10 : link 1 (float): per-component relative error of the PCA scores;
+      tail_exact                 : link 2 (exact): scikit-learn's MiniBatchKMeans + the reference's closeness / selection
+                                   run on the CPU from the GPU's OWN float32 embedding reproduce the GPU's labels, closeness
+                                   (1e-5) and - when the residuals `Z` are given or no singleton cluster needs them - list;
+      labels_equal / selected_equal / ari : end-to-end agreement, REPORTED (needs all ~1400 k-means++ draws to coincide, which
+                                   two float32 PCA implementations only achieve by chance - scripts/cpu_noise_floor.py)."""
+    from sklearn.metrics import adjusted_rand_score
+    rel = np.linalg.norm(gpu['X_pca'] - ref['X_pca'], axis=0) / np.linalg.norm(ref['X_pca'], axis=0)
+    labels_cpu, centers_cpu, _ = kmeans_genes(np.ascontiguousarray(gpu['X_pca']), n_var_clusters, random_state)
+    close_cpu = gene_closeness(np.ascontiguousarray(gpu['X_pca']), labels_cpu, centers_cpu)
+    same_labels = bool(np.array_equal(labels_cpu, gpu['labels']))
+    same_close = bool(np.allclose(close_cpu, gpu['closeness'], rtol=0, atol=1e-5))
+    has_single = bool((np.bincount(labels_cpu, minlength=n_var_clusters) == 1).any())
+    list_checked = Z is not None or not has_single
+    same_list = True
+    if list_checked:
+        same_list = bool(np.array_equal(np.asarray(gpu['selected']).astype(str),
+                                        select_fast(var_names, labels_cpu, np.asarray(gpu['closeness']), Z, True,
+                                                    random_state).astype(str)))
+    return {"pca_rel_err_max": float(rel.max()), "pca_rel_err_first10": float(rel[:10].max()),
+            "tail_exact": bool(same_labels and same_close and same_list),
+            "tail_labels_equal": same_labels, "tail_closeness_equal": same_close,
+            "tail_list_equal": same_list if list_checked else None,
+            "labels_equal": bool(np.array_equal(gpu['labels'], ref['labels'])),
+            "ari": float(adjusted_rand_score(gpu['labels'], ref['labels'])),
+            "selected_equal": bool(np.array_equal(np.asarray(gpu['selected']).astype(str), np.asarray(ref['selected']).astype(str))),
+            "selected_common": int(len(set(np.asarray(gpu['selected']).astype(str)) & set(np.asarray(ref['selected']).astype(str)))),
+            "n_selected": int(len(gpu['selected'])), "n_selected_ref": int(len(ref['selected']))}
+

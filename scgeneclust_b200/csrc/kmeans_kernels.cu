@@ -317,9 +317,6 @@ __device__ __forceinline__ float chain_sum(const float *q, int len, float acc) {
     return acc;
 }
 // Returns (to every thread of the CTA) whether this CTA ran the tail of the round.
-// PHASE_A = true: this CTA first computes the trial-distance tile of candidate blockIdx.y (grid = tiles x candidates);
-// PHASE_A = false: the caller has already written trial_dist / partial for ALL candidates of its tile (grid = tiles x 1).
-template <bool PHASE_A>
 __device__ __forceinline__ bool
 kpp_round_step(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
                const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
@@ -336,8 +333,8 @@ kpp_round_step(KppState *st, const float *__restrict__ X, int64_t ldx, const dou
     __shared__ float s_pot;
     __shared__ double s_rv[32];
     __shared__ int64_t s_found[32];
-    if (PHASE_A) {
-        const int c = blockIdx.y;
+    const int c = blockIdx.y;
+    {
         // cand[] and closest[] were written by the tail CTA of the previous round - in the persistent launch that is
         // another CTA of the SAME kernel, so they are read through L2 (ld.cg), never from a stale L1 line
         const float *xc = X + (int64_t)__ldcg(cand + c) * ldx;
@@ -545,73 +542,21 @@ kpp_round_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const d
                  const double *__restrict__ yy, int64_t n, int d, int32_t *cand,
                  float *closest, float *trial_dist, double *partial, const double *__restrict__ uniforms, int n_trials,
                  int32_t *__restrict__ indices_out, int round, int last_round, unsigned int *ticket) {
-    kpp_round_step<true>(st, X, ldx, Xt, yy, n, d, cand, closest, trial_dist, partial, uniforms, n_trials, indices_out, round,
-                         last_round, ticket);
+    kpp_round_step(st, X, ldx, Xt, yy, n, d, cand, closest, trial_dist, partial, uniforms, n_trials, indices_out, round,
+                   last_round, ticket);
 }
 
-// ALL greedy rounds in one cooperative launch (every CTA is resident, so CTAs may wait for one another).  One CTA per tile
-// of 256 samples, for all candidates of a round: a thread keeps the float64 coordinates of ITS sample in registers for
-// the whole kernel (the per-round launch re-read them from L2 for every candidate: 17 MB per round, the cost of the
-// distance phase), the candidates' coordinates sit in shared memory.  Per round the CTA that finishes its tile last runs
-// the sequential tail and then publishes the round number; the other CTAs wait for it.
+// ALL greedy rounds in one cooperative launch (every CTA is resident, so CTAs may wait for one another): per round the
+// CTA that finishes its distance tile last runs the sequential tail and then publishes the round number; the other CTAs
+// wait for it.  Saves the 198 launches and their inter-kernel gaps (~4 us each of the 23 us a round took).
 __global__ void __launch_bounds__(kKppThreads)
 kpp_persistent_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, const double *__restrict__ Xt,
                       const double *__restrict__ yy, int64_t n, int d, int32_t *cand, float *closest, float *trial_dist,
                       double *partial, const double *__restrict__ uniforms, int n_trials,
                       int32_t *__restrict__ indices_out, int K, unsigned int *ticket, int *round_flag) {
-    __shared__ float scand[32][kDMax];
-    __shared__ double sxx_c[32];
-    __shared__ double wred[32][kKppThreads / 32];
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool valid = i < n;
-    double xr[kDMax];
-#pragma unroll
-    for (int f = 0; f < kDMax; ++f) xr[f] = (valid && f < d) ? Xt[(int64_t)f * n + i] : 0.0;
-    const double yy_i = valid ? yy[i] : 0.0;
     for (int round = 1; round < K; ++round) {
-        // ---- distance phase: every candidate of the round against this CTA's samples
-        for (int e = threadIdx.x; e < n_trials * kDMax; e += blockDim.x) {
-            const int c = e / kDMax, f = e % kDMax;
-            scand[c][f] = f < d ? X[(int64_t)__ldcg(cand + c) * ldx + f] : 0.f;
-        }
-        __syncthreads();
-        if (threadIdx.x < n_trials) {
-            double xx = 0.0;
-            for (int f = 0; f < d; ++f) xx = fma((double)scand[threadIdx.x][f], (double)scand[threadIdx.x][f], xx);
-            sxx_c[threadIdx.x] = xx;
-        }
-        __syncthreads();
-        const float closest_i = valid ? __ldcg(closest + i) : 0.f;
-        for (int c = 0; c < n_trials; ++c) {
-            double dot = 0.0;
-#pragma unroll
-            for (int f = 0; f < kDMax; ++f) dot = fma((double)scand[c][f], xr[f], dot);   // zero padding beyond d: exact
-            double v = -2.0 * dot;
-            v = v + sxx_c[c];
-            v = v + yy_i;
-            float r = (float)v;
-            r = r > 0.f ? r : 0.f;
-            double contrib = 0.0;
-            if (valid) {
-                const float dd = fminf(closest_i, r);
-                trial_dist[(int64_t)c * n + i] = dd;
-                contrib = (double)dd;
-            }
-            // fixed-order CTA sum: warp tree, then the eight warp sums in order
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-            if ((threadIdx.x & 31) == 0) wred[c][threadIdx.x >> 5] = contrib;
-        }
-        __syncthreads();
-        if (threadIdx.x < n_trials) {
-            double sum = 0.0;
-            for (int w = 0; w < kKppThreads / 32; ++w) sum += wred[threadIdx.x][w];
-            partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = sum;
-        }
-        __syncthreads();
-        // ---- ticket, tail by the last CTA, hand-over
-        const bool ran_tail = kpp_round_step<false>(st, X, ldx, Xt, yy, n, d, cand, closest, trial_dist, partial, uniforms,
-                                                    n_trials, indices_out, round, round == K - 1 ? 1 : 0, ticket);
+        const bool ran_tail = kpp_round_step(st, X, ldx, Xt, yy, n, d, cand, closest, trial_dist, partial, uniforms, n_trials,
+                                             indices_out, round, round == K - 1 ? 1 : 0, ticket);
         if (round == K - 1) break;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -621,7 +566,7 @@ kpp_persistent_kernel(KppState *st, const float *__restrict__ X, int64_t ldx, co
             } else {
                 unsigned int spins = 0;
                 while (atomicAdd(round_flag, 0) < round) {        // L2 read; the tail takes a few microseconds
-                    __nanosleep(100);
+                    __nanosleep(200);
                     if (++spins > (1u << 24)) __trap();
                 }
                 __threadfence();
@@ -932,7 +877,7 @@ extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, i
         GC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         GC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kpp_persistent_kernel, kKppThreads, 0));
         static const bool no_persistent = getenv("GC_KPP_PER_ROUND") != nullptr;       // A/B switch for the tests
-        if (coop && !no_persistent && (int64_t)per_sm * kNumSMs >= (int64_t)n_blocks && K > 2) {
+        if (coop && !no_persistent && (int64_t)per_sm * kNumSMs >= (int64_t)n_blocks * n_trials && K > 2) {
             int *round_flag = (int *)(ticket + 16);
             GC_CUDA(cudaMemsetAsync(round_flag, 0, sizeof(int), st));
             int last_dummy = 0;
@@ -940,8 +885,7 @@ extern "C" int gc_kmeanspp_init(const float *X, int64_t ldx, int64_t n, int d, i
             void *args[] = {(void *)&state, (void *)&X, (void *)&ldx, (void *)&Xt, (void *)&yy, (void *)&n, (void *)&d,
                             (void *)&cand, (void *)&closest, (void *)&trial, (void *)&partial, (void *)&uniforms,
                             (void *)&n_trials, (void *)&indices_out, (void *)&K, (void *)&ticket, (void *)&round_flag};
-            GC_CUDA(cudaLaunchCooperativeKernel((const void *)kpp_persistent_kernel, dim3((unsigned)n_blocks, 1),
-                                                dim3(kKppThreads), args, 0, st));
+            GC_CUDA(cudaLaunchCooperativeKernel((const void *)kpp_persistent_kernel, grid, dim3(kKppThreads), args, 0, st));
             if (int rc = check_launch("kpp_persistent_kernel")) return rc;
         } else {
             for (int round = 1; round < K; ++round) {

@@ -39,7 +39,7 @@ def test_two_ranks_one_gpu_gloo_sharded_equals_single():
     _need_cuda()
     res = _torchrun(["12000", "5000", "--backend", "gloo", "--same-device"])
     assert res.returncode == 0, res.stdout[-2000:]
-    assert "selected list identical True" in res.stdout
+    assert "tail exact True" in res.stdout
 
 
 def test_two_ranks_host_csr_shards_gloo():
