@@ -32,7 +32,7 @@ __device__ __forceinline__ uint32_t mt_tw(uint32_t cur, uint32_t nxt) {
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
 
-// One CTA: emits n_words tempered outputs starting at position `pos` (0..624; 624 = regenerate first) of `state`.
+// One CTA: emits the n_words RAW (untempered) state words starting at position `pos` (0..624; 624 = regenerate first) of `state`.
 // A 624-word block is regenerated from the PREVIOUS block alone, all 624 words in parallel, one __syncthreads per block
 // (the textbook in-place loop needs three dependent phases: words [227, 454) read new words [0, 227), words [454, 624)
 // read new words [227, 397)).  Substituting the recurrence into itself removes the dependence on new words:
@@ -51,7 +51,7 @@ mt19937_stream_kernel(const uint32_t *__restrict__ state, int pos, int64_t n_wor
     int64_t done = 0;
     if (pos < kMtN) {          // words left in the current block
         const int avail = kMtN - pos;
-        for (int i = t; i < avail && i < n_words; i += blockDim.x) out[i] = mt_temper(buf[0][pos + i]);
+        for (int i = t; i < avail && i < n_words; i += blockDim.x) out[i] = buf[0][pos + i];       // RAW state words
         done = min((int64_t)avail, n_words);
     }
     int cur = 0;
@@ -70,7 +70,7 @@ mt19937_stream_kernel(const uint32_t *__restrict__ state, int pos, int64_t n_wor
                 v = mt[t - 57] ^ mt_tw(mt[t - 454], mt[t - 453]) ^ mt_tw(mt[t - 227], mt[t - 226]) ^ mt_tw(mt[t], nxt);
             }
             nt[t] = v;
-            if (t < left) out[done + t] = mt_temper(v);
+            if (t < left) out[done + t] = v;          // RAW: the (parallel) consumers temper on read
         }
         __syncthreads();
         done += min((int64_t)kMtN, left);
@@ -83,9 +83,11 @@ __device__ __forceinline__ double rk_double(uint32_t a, uint32_t b) {
 }
 // attempt i: x1, x2 in (-1, 1), accepted iff 0 < r2 < 1
 __device__ __forceinline__ bool polar_attempt(const uint32_t *__restrict__ w, int64_t i, double &x1, double &x2, double &r2) {
+    // the stream kernel stores the raw MT19937 state words (it is one CTA: every instruction it does not execute shortens
+    // the sequential part); the tempering of the output function happens here, in the massively parallel consumers
     const uint4 q = reinterpret_cast<const uint4 *>(w)[i];
-    x1 = 2.0 * rk_double(q.x, q.y) - 1.0;
-    x2 = 2.0 * rk_double(q.z, q.w) - 1.0;
+    x1 = 2.0 * rk_double(mt_temper(q.x), mt_temper(q.y)) - 1.0;
+    x2 = 2.0 * rk_double(mt_temper(q.z), mt_temper(q.w)) - 1.0;
     r2 = x1 * x1 + x2 * x2;
     return r2 < 1.0 && r2 != 0.0;
 }

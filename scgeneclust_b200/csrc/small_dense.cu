@@ -3,6 +3,8 @@
 // scGeneClust/pp/_preprocessing.py:52).  Kept on the device so the 16 passes run without host round trips.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gc {
 
 constexpr int kN = 64;
@@ -12,23 +14,24 @@ constexpr int kN = 64;
 // 1024 threads = 64 rows x 16 lanes: the length-j dot product of every row is split over 16 lanes (k = lane, lane+16,
 // ...) and folded with shuffles in a fixed order, so a column costs ~4 dependent FMAs instead of up to 60.  Same for
 // the forward substitutions of the inverse (one column of L^-1 per 16-lane group).
-constexpr int kCholThreads = 1024;
-__global__ void __launch_bounds__(kCholThreads)
+// LANES lanes per row (16: 1024 threads, 4: 256 threads - fewer warps make the three barriers per column cheaper).
+template <int LANES>
+__global__ void __launch_bounds__(kN * LANES)
 chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, int32_t *status) {
     extern __shared__ double dyn_smem[];
     double (*L)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem);
     double (*Li)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem + kN * (kN + 1));
     __shared__ double rdiag[kN];                                   // 1 / L[j][j]
-    const int i = threadIdx.x >> 4, t = threadIdx.x & 15;          // row / column owner, lane inside its 16-group
-    for (int j = t; j < kN; j += 16) { L[i][j] = (i < q && j < q) ? Gm[i * kN + j] : 0.0; Li[i][j] = 0.0; }
+    const int i = threadIdx.x / LANES, t = threadIdx.x % LANES;    // row / column owner, lane inside its group
+    for (int j = t; j < kN; j += LANES) { L[i][j] = (i < q && j < q) ? Gm[i * kN + j] : 0.0; Li[i][j] = 0.0; }
     __syncthreads();
     for (int j = 0; j < q; ++j) {
         double s = 0.0;
         if (i >= j && i < q) {
-            for (int k = t; k < j; k += 16) s = fma(L[i][k], L[j][k], s);
+            for (int k = t; k < j; k += LANES) s = fma(L[i][k], L[j][k], s);
         }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+        for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
         __syncthreads();                                            // all reads of column j's inputs are done
         if (t == 0 && i >= j && i < q) {
             double v = L[i][j] - s;
@@ -47,20 +50,20 @@ chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, 
     }
     // inverse of the lower-triangular L: the 16-lane group `i` solves column i of L X = I by forward substitution
     // (two groups share a warp and run different trip counts: group-wide masks)
-    const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
+    const unsigned gmask = (LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31) / LANES * LANES);
     if (i < q) {
         for (int r = i; r < q; ++r) {
             double s = 0.0;
-            for (int k = i + t; k < r; k += 16) s = fma(L[r][k], Li[k][i], s);
+            for (int k = i + t; k < r; k += LANES) s = fma(L[r][k], Li[k][i], s);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, 16);
+            for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, LANES);
             if (t == 0) Li[r][i] = ((r == i ? 1.0 : 0.0) - s) * rdiag[r];
             __syncwarp(gmask);
         }
     }
     __syncthreads();
     // Rinv[a][b] = (L^-1)^T[a][b] = Li[b][a]
-    for (int j = t; j < kN; j += 16) Rinv[i * kN + j] = (i < q && j < q) ? (float)Li[j][i] : 0.f;
+    for (int j = t; j < kN; j += LANES) Rinv[i * kN + j] = (i < q && j < q) ? (float)Li[j][i] : 0.f;
 }
 
 // Symmetric eigendecomposition of the leading q x q block of Gm by cyclic two-sided Jacobi with the round-robin
@@ -188,13 +191,18 @@ extern "C" int gc_chol_inv(const double *Gm, int q, float *Rinv, int32_t *status
     GC_REQUIRE(Gm && Rinv && status, "null pointer");
     GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
     const int smem = 2 * kN * (kN + 1) * (int)sizeof(double);
+    static const int lanes = []() { const char *e = getenv("GC_CHOL_LANES"); return e ? atoi(e) : 4; }();   // developer knob
     static thread_local bool configured[kMaxDevices] = {};
     const int dev_id = current_device();
     if (!configured[dev_id]) {
-        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[dev_id] = true;
     }
-    chol_inv_kernel<<<1, kCholThreads, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
+    if (lanes == 16) chol_inv_kernel<16><<<1, kN * 16, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
+    else if (lanes == 8) chol_inv_kernel<8><<<1, kN * 8, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
+    else chol_inv_kernel<4><<<1, kN * 4, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
     return check_launch("chol_inv_kernel");
 }
 
