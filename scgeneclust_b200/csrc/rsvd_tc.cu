@@ -553,16 +553,34 @@ rsvd_apply_tc_kernel(const TcArgs a) {
 }
 
 // Y[row, :] = sum_p partials[p][row, :]  -  out_shift[row] * colsum[0..63]  -  colsum[64..127]
-// (fixed summation order => deterministic; the last two terms are the implicit PCA centring, a rank-1 correction)
+// (fixed summation order => deterministic; the last two terms are the implicit PCA centring, a rank-1 correction).
+// n_ctas == 0: every slab wrote its own partial (slots 0 .. n_split-1).  n_ctas > 0 (the persistent TS kernel): a CTA
+// accumulates the consecutive slabs of a tile in registers and writes ONE partial per (tile, CTA), into the slot of the
+// first slab of its segment; the segments of tile t start at split 0 and wherever a CTA's item range
+// [floor(b n_items / n_ctas), floor((b+1) n_items / n_ctas)) begins inside the tile's items [t n_split, (t+1) n_split).
 __global__ void rsvd_tc_reduce_kernel(const float *__restrict__ partials, int64_t n_elem4, int n_split,
                                       const float *__restrict__ out_shift, const float *__restrict__ colsum,
-                                      float *__restrict__ Y) {
+                                      float *__restrict__ Y, int n_ctas, int64_t n_items) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_elem4) return;
     float4 s = reinterpret_cast<const float4 *>(partials)[i];
-    for (int p = 1; p < n_split; ++p) {
-        const float4 v = reinterpret_cast<const float4 *>(partials)[(int64_t)p * n_elem4 + i];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (n_ctas == 0) {
+        for (int p = 1; p < n_split; ++p) {
+            const float4 v = reinterpret_cast<const float4 *>(partials)[(int64_t)p * n_elem4 + i];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    } else {
+        const int64_t tile = (i >> 4) / TC_TM;                       // 16 float4 per output row, TC_TM rows per tile
+        const int64_t lo = tile * n_split, hi = lo + n_split;        // the tile's items
+        // first CTA whose range starts after `lo`:  floor(b n_items / n_ctas) > lo  <=>  b > ((lo + 1) n_ctas - 1) / n_items
+        int64_t b = ((lo + 1) * n_ctas - 1) / n_items + 1;
+        for (; b < n_ctas; ++b) {
+            const int64_t start = b * n_items / n_ctas;
+            if (start <= lo) continue;
+            if (start >= hi) break;
+            const float4 v = reinterpret_cast<const float4 *>(partials)[(start - lo) * n_elem4 + i];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
     }
     const int cg = (int)(i & 15);
     const float4 c1 = reinterpret_cast<const float4 *>(colsum)[cg];
@@ -722,8 +740,9 @@ static int rsvd_apply_impl(const gc_residual_matrix *M, int trans, const float *
     if (rc) return rc;
     if (int rc2 = check_launch("rsvd_apply_tc_kernel")) return rc2;
     const int64_t o4 = a.n_out * TC_TN / 4;
-    rsvd_tc_reduce_kernel<<<(unsigned)ceil_div<int64_t>(o4, 256), 256, 0, st>>>(a.partials, o4, a.n_split, out_shift,
-                                                                               s.colsum, Y);
+    const bool segmented = !(mode == 1 || force_ss);
+    rsvd_tc_reduce_kernel<<<(unsigned)ceil_div<int64_t>(o4, 256), 256, 0, st>>>(
+        a.partials, o4, a.n_split, out_shift, s.colsum, Y, segmented ? (int)grid.x : 0, n_tiles * a.n_split);
     return check_launch("rsvd_tc_reduce_kernel");
 }
 

@@ -44,20 +44,23 @@ namespace gc {
 #define TS_I2F_WORDS_N 1
 #endif
 constexpr int TS_I2F_WORDS = TS_I2F_WORDS_N;
+constexpr int TS_EPI_WARPS_N = 4;
 constexpr int TS_GROUPS = TS_GROUPS_N;                           // producer groups of four warps
 constexpr int TS_A_STAGES = TS_A_STAGES_N;                       // A-operand slots in tensor memory (64 columns each)
 constexpr int TS_PRODUCER_WARPS = 4 * TS_GROUPS;
-constexpr int TS_EPI_WARPS = 4;                                  // one per TMEM lane quarter
+constexpr int TS_EPI_WARPS = TS_EPI_WARPS_N;                     // one per TMEM lane quarter
 constexpr int TS_MMA_WARP = TS_PRODUCER_WARPS + TS_EPI_WARPS;
 constexpr int TS_THREADS = (TS_PRODUCER_WARPS + TS_EPI_WARPS + 3) * 32;
-constexpr int TS_RAW_STAGES = 9;                                 // raw count tiles in flight (TMA runs this far ahead)
+constexpr int TS_RAW_STAGES = 7;                                 // raw count tiles in flight (TMA runs this far ahead)
 constexpr int TS_B_STAGES = 4;
 constexpr int TS_RAW_BYTES = TC_TM * TC_TK * 2;                  // 16 KB raw uint16 tile
 constexpr int TS_PANEL_BYTES = 2 * TC_B_BYTES;                   // 16 KB [Q_hi | Q_lo]
 constexpr int TS_KC_BYTES = TC_TK * 4;                           // 256 B of per-k constants
 constexpr int TS_OFF_PANEL = TS_RAW_STAGES * TS_RAW_BYTES;
 constexpr int TS_OFF_KC = TS_OFF_PANEL + TS_B_STAGES * TS_PANEL_BYTES;
-constexpr int TS_OFF_BAR = TS_OFF_KC + TS_RAW_STAGES * TS_KC_BYTES;
+constexpr int TS_OFF_ACC = TS_OFF_KC + TS_RAW_STAGES * TS_KC_BYTES;         // epilogue running sums: 4 warps x 64 x 32 fp32
+constexpr int TS_ACC_BYTES = TS_EPI_WARPS_N * TC_TN * 32 * 4;
+constexpr int TS_OFF_BAR = TS_OFF_ACC + TS_ACC_BYTES;
 constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * TS_B_STAGES + 2;
 constexpr int TS_SMEM_BYTES = TS_OFF_BAR + 8 * TS_N_BARS + 16 + 1024 /*align*/;
 constexpr int TS_ACC_COLS = 192, TS_A_COLS = 64;   // D1 = [0, 128): A_hi [Q_hi | Q_lo];  D2 = [128, 192): A_lo Q_hi
@@ -210,7 +213,10 @@ __device__ __forceinline__ void split_pair(float z0, float z1, uint32_t &h, uint
 // and the epilogue of the previous item are still in flight.  Short slabs are what the accumulation accuracy wants
 // (kMaxSlabStages); with one CTA launch per slab their fixed costs (launch, TMEM allocation, pipeline fill and drain,
 // ~4 us) were 7 % of the pass at 48 stages per slab.
-// Item order: item = split * n_tiles + tile, so CTAs that run at the same time read the same panel k-range (L2 hits).
+// Item order: item = tile * n_split + split, and CTA b takes the CONTIGUOUS range [floor(b n_items / gridDim.x),
+// floor((b + 1) n_items / gridDim.x)): the slabs of a tile are consecutive items of (mostly) one CTA, whose epilogue warps
+// add the slab results in registers (round-to-nearest fp32) and write one partial per (tile, CTA) instead of one per slab
+// (at 32 stages per slab the per-slab partials were 130 MB per pass at config c3 and 470 MB per pass and GPU at config c5).
 template <int TRANS, int CLIP>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
@@ -229,9 +235,11 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     const int64_t n_items = n_tiles * a.n_split;
     // stages of an item: every slab has k_per_split / 64 stages except the last one of the k range
     auto item_stages = [&](int64_t item) -> int {
-        const int64_t k_lo = (item / n_tiles) * a.k_per_split, k_hi = min(a.n_k, k_lo + a.k_per_split);
+        const int64_t k_lo = (item % a.n_split) * a.k_per_split, k_hi = min(a.n_k, k_lo + a.k_per_split);
         return (int)ceil_div<int64_t>(max((int64_t)0, k_hi - k_lo), TC_TK);
     };
+    const int64_t item_begin = (int64_t)blockIdx.x * n_items / gridDim.x;
+    const int64_t item_end = ((int64_t)blockIdx.x + 1) * n_items / gridDim.x;
 
     if (warp == TS_MMA_WARP) {
         if (lane == 0) {
@@ -273,9 +281,9 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) chunk_off[c] = row_off + ((((uint32_t)c) ^ (uint32_t)(m & 7)) << 4);
         int64_t g0 = 0;                                            // stages of this CTA's earlier items
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int64_t item = item_begin; item < item_end; ++item) {
             const int n_it = item_stages(item);
-            const int64_t m0 = (item % n_tiles) * TC_TM;
+            const int64_t m0 = (item / a.n_split) * TC_TM;
             // the constant of this thread's output row (TRANS 0: r of its cell, TRANS 1: s/T of its gene); the padded
             // vectors hold 1.0 beyond the matrix, where TMA delivered zero counts: every residual stays finite
             const float fixed = __ldg((TRANS == 0 ? a.rpad : a.tpad) + m0 + m);
@@ -358,40 +366,61 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         const int quarter = warp - TS_PRODUCER_WARPS;
         const uint32_t t_lane = tmem_d + ((uint32_t)(quarter * 32) << 16);
         uint32_t ph = 0;
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        // this lane's output row, summed over the slabs of the segment, lives in shared memory (64 running sums per lane
+        // in registers pushed the whole kernel over its register budget): element j of lane l at [j][l], conflict free
+        const uint32_t acc_s = smem_base + TS_OFF_ACC + (uint32_t)quarter * (TC_TN * 32 * 4) + (uint32_t)lane * 4u;
+        for (int j = 0; j < TC_TN; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc_s + j * 128), "f"(0.f) : "memory");
+        int64_t seg_split = item_begin % a.n_split;                 // slot = split index of the segment's first slab
+        for (int64_t item = item_begin; item < item_end; ++item) {
             const int n_it = item_stages(item);
-            const int64_t row = (item % n_tiles) * TC_TM + quarter * 32 + lane;
-            const int64_t split = item / n_tiles;
-            float4 *dst = reinterpret_cast<float4 *>(a.partials + (split * a.n_out + row) * TC_TN);
             if (n_it > 0) {
                 mbar_wait_park(bar_acc_full, ph);
                 tc_fence_after();
-            }
 #pragma unroll 1
-            for (int cq = 0; cq < 4; ++cq) {
-                float acc[16];
+                for (int cq = 0; cq < 4; ++cq) {
+                    // fixed order inside a slab: hi.hi + hi.lo + lo.hi, then onto the running sum (round-to-nearest fp32)
+                    float t[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-                if (n_it > 0) {
+                    for (int j = 0; j < 16; ++j) t[j] = 0.f;
 #pragma unroll
                     for (int part = 0; part < 3; ++part) {
                         uint32_t v[16];
                         tmem_ld16(t_lane + (uint32_t)(part * 64 + cq * 16), v);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 16; ++j) t[j] += __uint_as_float(v[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float r;
+                        const uint32_t ad = acc_s + (uint32_t)(cq * 16 + j) * 128u;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(ad) : "memory");
+                        r += t[j];
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(r) : "memory");
                     }
                 }
-                if (row < a.n_out) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dst[cq * 4 + j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                }
-            }
-            if (n_it > 0) {
                 tc_fence_before();                                  // the TMEM reads before the next item's overwrite
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_free);
                 ph ^= 1;
+            }
+            const int64_t tile = item / a.n_split;
+            if (item + 1 == item_end || (item + 1) / a.n_split != tile) {      // last slab of this CTA's segment of the tile
+                const int64_t row = tile * TC_TM + quarter * 32 + lane;
+                float4 *dst = reinterpret_cast<float4 *>(a.partials + (seg_split * a.n_out + row) * TC_TN);
+#pragma unroll 4
+                for (int j = 0; j < TC_TN / 4; ++j) {
+                    float4 o;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.x) : "r"(acc_s + (4 * j) * 128) : "memory");
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.y) : "r"(acc_s + (4 * j + 1) * 128) : "memory");
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.z) : "r"(acc_s + (4 * j + 2) * 128) : "memory");
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o.w) : "r"(acc_s + (4 * j + 3) * 128) : "memory");
+                    if (row < a.n_out) dst[j] = o;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc_s + (4 * j) * 128), "f"(0.f) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc_s + (4 * j + 1) * 128), "f"(0.f) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc_s + (4 * j + 2) * 128), "f"(0.f) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(acc_s + (4 * j + 3) * 128), "f"(0.f) : "memory");
+                }
+                seg_split = 0;                                      // the next segment starts a new tile
             }
         }
     } else if (warp == TS_MMA_WARP) {
@@ -405,7 +434,7 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
         int64_t g0 = 0;
         uint32_t ph = 0;
-        for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int64_t item = item_begin; item < item_end; ++item) {
             const int n_it = item_stages(item);
             if (n_it == 0) continue;
             mbar_wait_park(bar_acc_free, ph ^ 1);                   // the previous item's accumulators have been read
@@ -430,9 +459,9 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         if (lane == 0) {
             const uint64_t policy = l2_evict_first_policy();
             int64_t g0 = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int64_t item = item_begin; item < item_end; ++item) {
                 const int n_it = item_stages(item);
-                const int64_t m0 = (item % n_tiles) * TC_TM, k_lo = (item / n_tiles) * a.k_per_split;
+                const int64_t m0 = (item / a.n_split) * TC_TM, k_lo = (item % a.n_split) * a.k_per_split;
                 const float *kconst = (TRANS == 0 ? a.tpad : a.rpad) + k_lo;
                 for (int it = 0; it < n_it; ++it) {
                     const int64_t gs = g0 + it;
@@ -452,9 +481,9 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
         // =============================== panel-tile copy issuer (one thread) ===============================
         if (lane == 0) {
             int64_t g0 = 0;
-            for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int64_t item = item_begin; item < item_end; ++item) {
                 const int n_it = item_stages(item);
-                const int64_t k_lo = (item / n_tiles) * a.k_per_split;
+                const int64_t k_lo = (item % a.n_split) * a.k_per_split;
                 const char *qh = reinterpret_cast<const char *>(a.Qh) + (k_lo / TC_TK) * TC_B_BYTES;
                 const char *ql = reinterpret_cast<const char *>(a.Ql) + (k_lo / TC_TK) * TC_B_BYTES;
                 for (int it = 0; it < n_it; ++it) {
