@@ -390,7 +390,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
                 break
         except Exception:  # noqa: BLE001
             pass
-    roofline = {"kernel": "rsvd_apply_tc_kernel (one Y = M Q / M^T Q pass over the implicit Pearson-residual matrix)",
+    roofline = {"kernel": "rsvd_apply_ts_kernel (one Y = M Q / M^T Q pass over the implicit Pearson-residual matrix)",
                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic,

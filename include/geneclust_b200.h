@@ -71,6 +71,12 @@ int gc_dense_to_counts(const float *src, int64_t ld_src, int64_t n_rows, int64_t
 /* col_max (G x uint32, zeroed by the caller, or NULL): the largest count of every gene. */
 int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, unsigned long long *row_sum,
                   unsigned long long *col_sum, uint32_t *col_max, void *stream);
+/* Derived statistics of the exact sums (row_sum already all-reduced on gene-sharded input): float32 copies, and
+ * head[4] (int64) = { total count, any all-zero gene, any all-zero cell, clip proof failed: some residual MAY reach
+ * +clip }.  scratch: 3 * 148 int64.  Replaces the reference's X.sum(0) / X.sum(1) / X.sum() bookkeeping inside
+ * scanpy's normalize_pearson_residuals (reached from scGeneClust/pp/_preprocessing.py:29). */
+int gc_count_stats(const long long *row_sum, int64_t C, const long long *col_sum, const uint32_t *col_max, int64_t G,
+                   double clip, float *row_sum_f, float *col_sum_f, long long *head, long long *scratch, void *stream);
 /* Materialise Z (float32, C x G, leading dimension ldz) - used by the ps path, which needs adata.X = residuals
  * (scGeneClust/tl/information.py:46,119), and by tests. */
 int gc_pearson_residuals(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, const float *row_sum_f,

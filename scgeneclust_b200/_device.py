@@ -200,21 +200,24 @@ class ResidualOperator:
         n_cells = counts.C
         if comm is not None:
             comm.all_reduce_sum(row_sum)
-        # one read-back: [total, any all-zero gene, any all-zero cell]; the all-zero-gene test is rank-local on sharded
-        # input, so it is max-reduced - every rank must raise together or the others hang in the next collective
-        bad = torch.stack([(col_sum == 0).any(), (row_sum == 0).any()]).to(torch.int64)
-        if comm is not None:
-            comm.all_reduce_max(bad)
         # Can a residual reach the upper clip sqrt(C)?  z = (x - mu) / sqrt(mu (1 + mu/theta)) < x / sqrt(mu), and
         # mu = r_c s_g / T >= r_min s_g / T, so gene g cannot if  x_max(g) / sqrt(r_min s_g / T) < clip.  When this holds for
         # every gene (typical: a count that large needs an outlier cell), the pass kernels skip the per-entry clip test;
-        # the result is the same, proved rather than assumed.  One extra G-vector reduction, no extra synchronisation.
+        # the result is the same, proved rather than assumed.
         clip = float(np.float32(np.sqrt(n_cells)))
-        total_d = row_sum.sum().to(torch.float64)
-        mu_min = row_sum.min().to(torch.float64) * col_sum.to(torch.float64) / total_d
-        worst = (col_max.to(torch.float64) / torch.sqrt(mu_min)).nan_to_num(nan=float("inf")).max()
-        may_clip = (worst >= 0.999 * clip).to(torch.int64).reshape(1)
-        head = torch.cat([row_sum.sum().reshape(1), bad, may_clip]).cpu().numpy()
+        # one call, one read-back: float32 copies of the sums and head = [total, any all-zero gene, any all-zero cell,
+        # clip proof failed]
+        row_sum_f = torch.empty(counts.C, dtype=torch.float32, device=dev)
+        col_sum_f = torch.empty(counts.G, dtype=torch.float32, device=dev)
+        head_d = torch.empty(4, dtype=torch.int64, device=dev)
+        scratch = torch.empty(3 * 148, dtype=torch.int64, device=dev)
+        L.count_stats(ptr(row_sum), counts.C, ptr(col_sum), ptr(col_max), counts.G, clip, ptr(row_sum_f),
+                      ptr(col_sum_f), ptr(head_d), ptr(scratch), stream_handle())
+        if comm is not None:
+            # the all-zero tests are rank-local on sharded input: every rank must raise together or the others hang in
+            # the next collective (the clip flag may differ between ranks: each picks its own kernel variant)
+            comm.all_reduce_max(head_d[1:3])
+        head = head_d.cpu().numpy()
         total = float(head[0])
         if total <= 0:
             raise ValueError("count matrix is empty")
@@ -222,8 +225,8 @@ class ResidualOperator:
             # the reference yields NaN residuals here (0/0) and sklearn PCA then raises on NaN input
             raise ValueError("Input contains all-zero genes or cells: Pearson residuals would be NaN. "
                              "Filter them first (the reference's loader uses min_cells=3).")
-        return cls(counts, row_sum, col_sum, row_sum.to(torch.float32), col_sum.to(torch.float32),
-                   total, float(theta), clip, upper_clip_inactive=not bool(head[3]))
+        return cls(counts, row_sum, col_sum, row_sum_f, col_sum_f, total, float(theta), clip,
+                   upper_clip_inactive=not bool(head[3]))
 
     def struct(self, row_shift=None, col_shift=None) -> ResidualMatrix:
         return ResidualMatrix(ptr(self.counts.data), self.C, self.G, self.counts.ld, ptr(self.row_sum_f),
@@ -346,6 +349,27 @@ def _side_stream(dev) -> "torch.cuda.Stream":
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
     return _SIDE_STREAMS[key]
+
+
+class HostCopy:
+    """Device tensor -> ndarray in pinned host memory, copied on the side stream so that the kernels queued after it on
+    the main stream do not wait for PCIe.  `array` is valid after `wait()`."""
+
+    def __init__(self, t: torch.Tensor):
+        t = t.contiguous()
+        self._pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        side = _side_stream(t.device)
+        side.wait_stream(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(side):
+            self._pin.copy_(t, non_blocking=True)
+            self._done = torch.cuda.Event()
+            self._done.record(side)
+        t.record_stream(side)
+        self.array = self._pin.numpy()          # shares the pinned buffer (kept alive by the array's base)
+
+    def wait(self) -> np.ndarray:
+        self._done.synchronize()
+        return self.array
 
 
 def device_normal_panel(random_state: int, rows: int, q: int, device) -> torch.Tensor:

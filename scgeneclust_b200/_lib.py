@@ -36,6 +36,7 @@ SIGNATURES = {
     "gc_csr_to_counts": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _i64, C.c_int, _p, _p]),
     "gc_dense_to_counts": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "gc_count_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "gc_count_stats": (C.c_int, [_p, _i64, _p, _p, _i64, C.c_double, _p, _p, _p, _p, _p]),
     "gc_pearson_residuals": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _f32, _f32, _f32, _p, _i64, _p]),
     "gc_residual_sums": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _f32, _f32, _f32, _p, _p, _p]),
     "gc_rsvd_scratch_bytes": (_i64, [_i64, _i64]),

@@ -73,12 +73,13 @@ def scGeneClust(
     pp.get_state(copied_adata).dense_redundancy = bool(return_info)
     # preprocessing: residuals stay an implicit device operator for `fast`; `ps` and `return_info` need them dense
     pp.normalize(copied_adata, modality, materialize=(version == 'ps' or return_info))
-    pp.reduce_dim(copied_adata, version, random_state)
+    pp.reduce_dim(copied_adata, version, random_state, defer_host_copy=True)
     # gene clustering
     tl.cluster_genes(copied_adata, image, version, modality, shape, n_var_clusters, n_obs_clusters, n_components,
                      relevant_gene_pct, max_workers, random_state)
     # select features from gene clusters
     selected_genes = tl.select_from_clusters(copied_adata, version, post_hoc_filtering, random_state)
+    pp.finish_host_copies(copied_adata)
     check_all_genes_selected(raw_adata, selected_genes)
 
     if subset:

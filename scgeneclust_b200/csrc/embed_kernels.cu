@@ -360,12 +360,29 @@ __host__ inline int choose_split(int64_t n_tiles, int64_t n_k) {
 // ---------------------------------------------------------------------------------------------------------
 // tall-skinny panel algebra (rows x 64 float32 panels)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kGramRowsPerCta = 512;
-__global__ void __launch_bounds__(256)
-panel_gram_partial_kernel(const float *__restrict__ P, int64_t rows, double *__restrict__ partial) {
+// Gram P^T P in float64.  The 64 x 64 result is a 16 x 16 grid of 4 x 4 blocks; only the 136 blocks on or above the
+// diagonal are computed (one thread each, 160-thread CTAs), the reduce kernel mirrors them.  The row range is split
+// over up to 296 CTAs (two per SM): round 1's fixed 512 rows per CTA left a third of the SMs idle on a 50 000-row panel
+// and made each CTA's float64 FMA chain 512 rows long (47 us per Gram, 17 per selection).
+constexpr int kGramMaxCtas = 296;
+constexpr int kGramThreads = 160;
+constexpr int kGramBlocks = 136;
+
+__host__ __device__ inline int64_t gram_rows_per_cta(int64_t rows) {
+    const int64_t per = (rows + kGramMaxCtas - 1) / kGramMaxCtas;
+    return ((per + 31) / 32) * 32;
+}
+
+__global__ void __launch_bounds__(kGramThreads)
+panel_gram_partial_kernel(const float *__restrict__ P, int64_t rows, int64_t rows_per_cta, double *__restrict__ partial) {
     __shared__ __align__(16) float sP[32][kQ];
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    const int64_t r_lo = (int64_t)blockIdx.x * kGramRowsPerCta, r_hi = min(rows, r_lo + kGramRowsPerCta);
+    const int t = threadIdx.x;
+    const bool active = t < kGramBlocks;
+    // block (ty, tx), ty <= tx, row-major over the upper triangle
+    int ty = 0, rem = t;
+    while (active && rem >= 16 - ty) { rem -= 16 - ty; ++ty; }
+    const int tx = active ? ty + rem : 0;
+    const int64_t r_lo = (int64_t)blockIdx.x * rows_per_cta, r_hi = min(rows, r_lo + rows_per_cta);
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -373,25 +390,27 @@ panel_gram_partial_kernel(const float *__restrict__ P, int64_t rows, double *__r
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     for (int64_t r0 = r_lo; r0 < r_hi; r0 += 32) {
         __syncthreads();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int idx = threadIdx.x + h * 256, rr = idx >> 4, c4 = idx & 15;
+        for (int idx = t; idx < 32 * 16; idx += kGramThreads) {
+            const int rr = idx >> 4, c4 = idx & 15;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r0 + rr < r_hi) v = *reinterpret_cast<const float4 *>(P + (r0 + rr) * kQ + c4 * 4);
             *reinterpret_cast<float4 *>(&sP[rr][c4 * 4]) = v;
         }
         __syncthreads();
+        if (active) {
 #pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-            const float4 av = *reinterpret_cast<const float4 *>(&sP[rr][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4 *>(&sP[rr][tx * 4]);
-            const double am[4] = {av.x, av.y, av.z, av.w}, bm[4] = {bv.x, bv.y, bv.z, bv.w};
+            for (int rr = 0; rr < 32; ++rr) {
+                const float4 av = *reinterpret_cast<const float4 *>(&sP[rr][ty * 4]);
+                const float4 bv = *reinterpret_cast<const float4 *>(&sP[rr][tx * 4]);
+                const double am[4] = {av.x, av.y, av.z, av.w}, bm[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(am[i], bm[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(am[i], bm[j], acc[i][j]);
+            }
         }
     }
+    if (!active) return;
     double *out = partial + (int64_t)blockIdx.x * kQ * kQ;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -399,11 +418,15 @@ panel_gram_partial_kernel(const float *__restrict__ P, int64_t rows, double *__r
         for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * kQ + tx * 4 + j] = acc[i][j];
 }
 
+// fixed summation order over the partials; entries of a block below the diagonal are read from the mirrored block
 __global__ void panel_gram_reduce_kernel(const double *__restrict__ partial, int n_part, double *__restrict__ Gm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kQ * kQ) return;
+    const int r = i / kQ, c = i % kQ;
+    const int src = (r >> 2) <= (c >> 2) ? i : c * kQ + r;
     double s = 0.0;
-    for (int p = 0; p < n_part; ++p) s += partial[(int64_t)p * kQ * kQ + i];
+#pragma unroll 8
+    for (int p = 0; p < n_part; ++p) s += partial[(int64_t)p * kQ * kQ + src];
     Gm[i] = s;
 }
 
@@ -517,6 +540,78 @@ static int check_counts_layout(const uint16_t *counts, int64_t C, int64_t G, int
     return 0;
 }
 
+namespace gc {
+// Statistics the operator needs from the exact sums, in two launches instead of ~20 framework calls:
+// rows: float32 copies, per-CTA (total, min, any zero);  finish: the reductions of those, float32 gene sums, any
+// all-zero gene, and the clip proof  max_g x_max(g) / sqrt(r_min s_g / T)  >= 0.999 clip  (see ResidualOperator).
+constexpr int kStatCtas = 148;
+__global__ void __launch_bounds__(256)
+count_stats_rows_kernel(const long long *__restrict__ row_sum, int64_t C, float *__restrict__ row_sum_f,
+                        long long *__restrict__ part) {
+    long long tot = 0, mn = 0x7fffffffffffffffLL, zero = 0;
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < C; c += (int64_t)gridDim.x * 256) {
+        const long long v = row_sum[c];
+        row_sum_f[c] = (float)v;
+        tot += v; mn = v < mn ? v : mn; zero |= (v == 0);
+    }
+    __shared__ long long s_tot[256], s_mn[256], s_zero[256];
+    s_tot[threadIdx.x] = tot; s_mn[threadIdx.x] = mn; s_zero[threadIdx.x] = zero;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_tot[threadIdx.x] += s_tot[threadIdx.x + o];
+            s_mn[threadIdx.x] = min(s_mn[threadIdx.x], s_mn[threadIdx.x + o]);
+            s_zero[threadIdx.x] |= s_zero[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 3 + 0] = s_tot[0]; part[blockIdx.x * 3 + 1] = s_mn[0]; part[blockIdx.x * 3 + 2] = s_zero[0];
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+count_stats_finish_kernel(const long long *__restrict__ part, int n_part, const long long *__restrict__ col_sum,
+                          const uint32_t *__restrict__ col_max, int64_t G, double clip, float *__restrict__ col_sum_f,
+                          long long *__restrict__ head) {
+    __shared__ long long s_tot, s_mn, s_zero;
+    __shared__ double s_worst[1024];
+    __shared__ int s_gzero[1024];
+    if (threadIdx.x == 0) {
+        long long tot = 0, mn = 0x7fffffffffffffffLL, zero = 0;
+        for (int p = 0; p < n_part; ++p) {
+            tot += part[p * 3]; mn = min(mn, part[p * 3 + 1]); zero |= part[p * 3 + 2];
+        }
+        s_tot = tot; s_mn = mn; s_zero = zero;
+    }
+    __syncthreads();
+    const double total = (double)s_tot, r_min = (double)s_mn;
+    double worst = 0.0;
+    int gzero = 0;
+    for (int64_t g = threadIdx.x; g < G; g += 1024) {
+        const long long sg = col_sum[g];
+        col_sum_f[g] = (float)sg;
+        gzero |= (sg == 0);
+        const double mu_min = r_min * (double)sg / total;
+        double w = (double)col_max[g] / sqrt(mu_min);
+        if (!(w == w)) w = INFINITY;                       // 0 / 0: an all-zero gene or cell (raised by the caller anyway)
+        worst = fmax(worst, w);
+    }
+    s_worst[threadIdx.x] = worst; s_gzero[threadIdx.x] = gzero;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_worst[threadIdx.x] = fmax(s_worst[threadIdx.x], s_worst[threadIdx.x + o]);
+            s_gzero[threadIdx.x] |= s_gzero[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        head[0] = s_tot; head[1] = s_gzero[0]; head[2] = s_zero; head[3] = s_worst[0] >= 0.999 * clip;
+    }
+}
+}  // namespace gc
+
 extern "C" int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, unsigned long long *row_sum,
                              unsigned long long *col_sum, uint32_t *col_max, void *stream) {
     if (int rc = check_counts_layout(counts, C, G, ld)) return rc;
@@ -524,6 +619,19 @@ extern "C" int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64
     dim3 grid((unsigned)ceil_div<int64_t>(ld, 2048), (unsigned)ceil_div<int64_t>(C, kSumRows));
     count_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(counts, C, G, ld, row_sum, col_sum, col_max);
     return check_launch("count_sums_kernel");
+}
+
+extern "C" int gc_count_stats(const long long *row_sum, int64_t C, const long long *col_sum, const uint32_t *col_max,
+                              int64_t G, double clip, float *row_sum_f, float *col_sum_f, long long *head,
+                              long long *scratch, void *stream) {
+    GC_REQUIRE(row_sum && col_sum && col_max && row_sum_f && col_sum_f && head && scratch, "null pointer");
+    GC_REQUIRE(C >= 1 && G >= 1, "empty matrix");
+    const int n_part = (int)std::min<int64_t>(kStatCtas, ceil_div<int64_t>(C, 256));
+    count_stats_rows_kernel<<<n_part, 256, 0, as_stream(stream)>>>(row_sum, C, row_sum_f, scratch);
+    if (int rc = check_launch("count_stats_rows_kernel")) return rc;
+    count_stats_finish_kernel<<<1, 1024, 0, as_stream(stream)>>>(scratch, n_part, col_sum, col_max, G, clip, col_sum_f,
+                                                                 head);
+    return check_launch("count_stats_finish_kernel");
 }
 
 extern "C" int gc_pearson_residuals(const uint16_t *counts, int64_t C, int64_t G, int64_t ld, const float *row_sum_f,
@@ -618,7 +726,8 @@ extern "C" int gc_rsvd_apply_simt(const gc_residual_matrix *M, int trans, const 
 }
 
 extern "C" int64_t gc_gram_scratch_bytes(int64_t rows) {
-    const int64_t n_part = ceil_div<int64_t>(rows, kGramRowsPerCta);
+    // upper bound of the partial count for every row count <= rows (a shorter panel may use more, smaller slices)
+    const int64_t n_part = std::min<int64_t>(kGramMaxCtas, ceil_div<int64_t>(rows, 32));
     const int64_t n_cta64 = ceil_div<int64_t>(rows, 64);
     const int64_t a = n_part * kQ * kQ * 8, b = n_cta64 * kQ * (4 + 8);
     return (a > b ? a : b) + 256;
@@ -626,8 +735,9 @@ extern "C" int64_t gc_gram_scratch_bytes(int64_t rows) {
 
 extern "C" int gc_panel_gram(const float *P, int64_t rows, double *Gm, void *scratch, void *stream) {
     GC_REQUIRE(P && Gm && scratch && rows >= 1, "bad arguments");
-    const int n_part = (int)ceil_div<int64_t>(rows, kGramRowsPerCta);
-    panel_gram_partial_kernel<<<n_part, 256, 0, as_stream(stream)>>>(P, rows, (double *)scratch);
+    const int64_t per = gram_rows_per_cta(rows);
+    const int n_part = (int)ceil_div<int64_t>(rows, per);
+    panel_gram_partial_kernel<<<n_part, kGramThreads, 0, as_stream(stream)>>>(P, rows, per, (double *)scratch);
     if (int rc = check_launch("panel_gram_partial_kernel")) return rc;
     panel_gram_reduce_kernel<<<kQ * kQ / 256, 256, 0, as_stream(stream)>>>((const double *)scratch, n_part, Gm);
     return check_launch("panel_gram_reduce_kernel");

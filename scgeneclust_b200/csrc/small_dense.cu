@@ -11,65 +11,69 @@ constexpr int kN = 64;
 
 // Cholesky Gm = L L^T of the leading q x q block, then Rinv = (L^-1)^T as float32 (64 x 64, zero padded), so that
 // P @ Rinv has orthonormal columns when Gm = P^T P.  status[0] |= 1 on a non-positive pivot.
-// 1024 threads = 64 rows x 16 lanes: the length-j dot product of every row is split over 16 lanes (k = lane, lane+16,
-// ...) and folded with shuffles in a fixed order, so a column costs ~4 dependent FMAs instead of up to 60.  Same for
-// the forward substitutions of the inverse (one column of L^-1 per 16-lane group).
-// LANES lanes per row (16: 1024 threads, 4: 256 threads - fewer warps make the three barriers per column cheaper).
-template <int LANES>
-__global__ void __launch_bounds__(kN * LANES)
+//
+// Right-looking (outer-product) Cholesky fused with the column-oriented forward substitution L X = I, ONE barrier per
+// column.  At step j the Schur complement A holds the pivot column j; with rs = 1/sqrt(A[j][j]) the column of L is
+// A[:, j] rs and row j of L^-1 is Xraw[j][:] rs.  Both updates of step j,
+//     A[i][k] -= (A[i][j] rs) (A[k][j] rs)        j < k <= i
+//     X[i][c] -= (A[i][j] rs) (Xraw[j][c] rs)     c <= j < i
+// read only column j of A and row j of X, which step j does not write (they keep their unscaled values for good: the
+// scaling by rs is applied once, when Rinv is written), and write only entries no other thread of the step reads.
+// 1024 threads = 64 rows x 16 lanes, four columns each.  (Round 1's left-looking version needed three barriers per
+// column plus a sequential substitution: 62 us per call, 16 calls per selection.)
+__global__ void __launch_bounds__(1024)
 chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, int32_t *status) {
     extern __shared__ double dyn_smem[];
-    double (*L)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem);
-    double (*Li)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem + kN * (kN + 1));
+    double (*A)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem);
+    double (*X)[kN + 1] = reinterpret_cast<double (*)[kN + 1]>(dyn_smem + kN * (kN + 1));
     __shared__ double rdiag[kN];                                   // 1 / L[j][j]
-    const int i = threadIdx.x / LANES, t = threadIdx.x % LANES;    // row / column owner, lane inside its group
-    for (int j = t; j < kN; j += LANES) { L[i][j] = (i < q && j < q) ? Gm[i * kN + j] : 0.0; Li[i][j] = 0.0; }
+    const int i = threadIdx.x >> 4, l = threadIdx.x & 15;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int c = l + 16 * m;
+        A[i][c] = (i < q && c < q) ? Gm[i * kN + c] : 0.0;
+        X[i][c] = i == c ? 1.0 : 0.0;
+    }
     __syncthreads();
     for (int j = 0; j < q; ++j) {
-        double s = 0.0;
-        if (i >= j && i < q) {
-            for (int k = t; k < j; k += LANES) s = fma(L[i][k], L[j][k], s);
+        double piv = A[j][j];
+        if (!(piv > 0.0)) {
+            if (threadIdx.x == 0) atomicOr(status, 1);
+            piv = 1.0;
         }
+        const double rs = rsqrt(piv);
+        if (threadIdx.x == 0) rdiag[j] = rs;
+        if (i > j && i < q) {
+            const double w = -(A[i][j] * (rs * rs));
 #pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
-        __syncthreads();                                            // all reads of column j's inputs are done
-        if (t == 0 && i >= j && i < q) {
-            double v = L[i][j] - s;
-            if (i == j) {
-                if (!(v > 0.0)) { atomicOr(status, 1); v = 1.0; }
-                const double rs = rsqrt(v);                         // one reciprocal square root per column: the rows
-                rdiag[j] = rs;                                      // multiply by it instead of dividing by the pivot
-                L[j][j] = v * rs;
-            } else {
-                L[i][j] = v;
+            for (int m = 0; m < 4; ++m) {
+                const int c = l + 16 * m;
+                if (c <= j) X[i][c] = fma(w, X[j][c], X[i][c]);
+                else if (c <= i) A[i][c] = fma(w, A[c][j], A[i][c]);
             }
         }
         __syncthreads();
-        if (t == 0 && i > j && i < q) L[i][j] = L[i][j] * rdiag[j];
-        __syncthreads();
     }
-    // inverse of the lower-triangular L: the 16-lane group `i` solves column i of L X = I by forward substitution
-    // (two groups share a warp and run different trip counts: group-wide masks)
-    const unsigned gmask = (LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31) / LANES * LANES);
-    if (i < q) {
-        for (int r = i; r < q; ++r) {
-            double s = 0.0;
-            for (int k = i + t; k < r; k += LANES) s = fma(L[r][k], Li[k][i], s);
+    // Rinv[a][b] = (L^-1)[b][a] = Xraw[b][a] / L[b][b]   (a <= b)
 #pragma unroll
-            for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(gmask, s, o, LANES);
-            if (t == 0) Li[r][i] = ((r == i ? 1.0 : 0.0) - s) * rdiag[r];
-            __syncwarp(gmask);
-        }
+    for (int m = 0; m < 4; ++m) {
+        const int c = l + 16 * m;
+        Rinv[i * kN + c] = (i < q && c < q && i <= c) ? (float)(X[c][i] * rdiag[c]) : 0.f;
     }
-    __syncthreads();
-    // Rinv[a][b] = (L^-1)^T[a][b] = Li[b][a]
-    for (int j = t; j < kN; j += LANES) Rinv[i * kN + j] = (i < q && j < q) ? (float)Li[j][i] : 0.f;
 }
 
 // Symmetric eigendecomposition of the leading q x q block of Gm by cyclic two-sided Jacobi with the round-robin
 // parallel ordering.  Outputs eigenvalues in descending order (evals[64], zero padded) and the matching
 // eigenvectors as columns of U (float32 and float64, 64 x 64 row-major, zero padded).
-constexpr int kEigThreads = 1024;   // ~1800 row/column updates per Jacobi round: two per thread
+//
+// A round has two barriers.  (1) One thread per pair (a, b) forms its rotation.  The angle is formed in float32
+// (t = sgn(tau) / (|tau| + sqrt(1 + tau^2)) from the float32 casts of the three entries) and then c = rsqrt(1 + t^2),
+// s = t c in float64: the rotation is orthogonal to float64 accuracy, the annihilated entry is left at ~1e-7 of its
+// size instead of 0, which the next sweep removes - the sweep count is the same, and the float64 divide / sqrt chains
+// (~5 x 150 cycles, the serial part of every round) are gone.  (2) A <- J^T A J is done 2 x 2 block-wise: the pairs
+// partition the indices, so block (pair i, pair j) is read and written by one thread only, with both rotations
+// applied in registers; V <- V J runs in the same phase.
+constexpr int kEigThreads = 1024;
 __global__ void __launch_bounds__(kEigThreads)
 sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals, float *__restrict__ U32,
                double *__restrict__ U64) {
@@ -89,6 +93,10 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
         A[r][c] = (r < q && c < q) ? Gm[r * kN + c] : 0.0;
         V[r][c] = r == c ? 1.0 : 0.0;
     }
+    // fixed work assignment: one 2 x 2 block of A per thread, row vr of V for pairs vp0 and vp0 + 16
+    const int bi = tid / n_pairs, bj = tid % n_pairs;
+    const bool has_block = bi < n_pairs;
+    const int vr = tid & (kN - 1), vp0 = tid >> 6;
     __syncthreads();
     for (int sweep = 0; sweep < 30; ++sweep) {
         // off-diagonal / diagonal squared norms: thread r < q sums its row, thread 0 adds the q row sums in order
@@ -114,35 +122,42 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
                 int b = (round + m - 1 - tid) % (m - 1);
                 if (a > b) { const int t = a; a = b; b = t; }
                 double c = 1.0, s = 0.0;
-                if (b < q && A[a][b] != 0.0) {
-                    const double apq = A[a][b], tau = (A[b][b] - A[a][a]) / (2.0 * apq);
-                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    c = 1.0 / sqrt(1.0 + t * t);
-                    s = t * c;
+                if (b < q) {
+                    const float apq = (float)A[a][b], diff = (float)(A[b][b] - A[a][a]);
+                    if (apq != 0.f) {
+                        const float tau = diff / (2.f * apq);
+                        const float tf = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+                        if (tf == tf) {                                  // inf / inf cannot occur; guard anyway
+                            const double t = (double)tf;
+                            c = rsqrt(1.0 + t * t);
+                            s = t * c;
+                        }
+                    }
                 }
                 pp[tid] = a; qq[tid] = b; cs[tid][0] = c; cs[tid][1] = s;
             }
             __syncthreads();
-            // A <- A J  (columns), V <- V J
-            for (int task = tid; task < n_pairs * q; task += kEigThreads) {
-                const int pr = task / q, r = task % q;
-                const int a = pp[pr], b = qq[pr];
-                if (b >= q) continue;
-                const double c = cs[pr][0], s = cs[pr][1];
-                const double x = A[r][a], y = A[r][b];
-                A[r][a] = c * x - s * y; A[r][b] = s * x + c * y;
-                const double vx = V[r][a], vy = V[r][b];
-                V[r][a] = c * vx - s * vy; V[r][b] = s * vx + c * vy;
+            if (has_block) {
+                const int ai = pp[bi], bi_ = qq[bi], aj = pp[bj], bj_ = qq[bj];
+                const double ci = cs[bi][0], si = cs[bi][1], cj = cs[bj][0], sj = cs[bj][1];
+                const double x00 = A[ai][aj], x01 = A[ai][bj_], x10 = A[bi_][aj], x11 = A[bi_][bj_];
+                // columns (pair j), then rows (pair i)
+                const double y00 = cj * x00 - sj * x01, y01 = sj * x00 + cj * x01;
+                const double y10 = cj * x10 - sj * x11, y11 = sj * x10 + cj * x11;
+                A[ai][aj] = ci * y00 - si * y10;  A[ai][bj_] = ci * y01 - si * y11;
+                A[bi_][aj] = si * y00 + ci * y10; A[bi_][bj_] = si * y01 + ci * y11;
             }
-            __syncthreads();
-            // A <- J^T A  (rows)
-            for (int task = tid; task < n_pairs * q; task += kEigThreads) {
-                const int pr = task / q, col = task % q;
-                const int a = pp[pr], b = qq[pr];
-                if (b >= q) continue;
-                const double c = cs[pr][0], s = cs[pr][1];
-                const double x = A[a][col], y = A[b][col];
-                A[a][col] = c * x - s * y; A[b][col] = s * x + c * y;
+            if (vr < q) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pr = vp0 + 16 * h;
+                    if (pr < n_pairs) {
+                        const int a = pp[pr], b = qq[pr];
+                        const double c = cs[pr][0], s = cs[pr][1];
+                        const double vx = V[vr][a], vy = V[vr][b];
+                        V[vr][a] = c * vx - s * vy; V[vr][b] = s * vx + c * vy;
+                    }
+                }
             }
             __syncthreads();
         }
@@ -191,18 +206,13 @@ extern "C" int gc_chol_inv(const double *Gm, int q, float *Rinv, int32_t *status
     GC_REQUIRE(Gm && Rinv && status, "null pointer");
     GC_REQUIRE(q >= 1 && q <= kN, "q must be in [1, 64]");
     const int smem = 2 * kN * (kN + 1) * (int)sizeof(double);
-    static const int lanes = []() { const char *e = getenv("GC_CHOL_LANES"); return e ? atoi(e) : 8; }();   // developer knob (4 / 8 / 16 measured alike)
     static thread_local bool configured[kMaxDevices] = {};
     const int dev_id = current_device();
     if (!configured[dev_id]) {
-        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GC_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[dev_id] = true;
     }
-    if (lanes == 16) chol_inv_kernel<16><<<1, kN * 16, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
-    else if (lanes == 8) chol_inv_kernel<8><<<1, kN * 8, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
-    else chol_inv_kernel<4><<<1, kN * 4, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
+    chol_inv_kernel<<<1, 1024, smem, as_stream(stream)>>>(Gm, q, Rinv, status);
     return check_launch("chol_inv_kernel");
 }
 

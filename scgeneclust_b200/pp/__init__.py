@@ -1,1 +1,1 @@
-from ._preprocessing import get_state, normalize, reduce_dim, start_omega
+from ._preprocessing import finish_host_copies, get_state, normalize, reduce_dim, start_omega

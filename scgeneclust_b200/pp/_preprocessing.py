@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from loguru import logger
 
-from .._device import (DeviceCounts, ResidualOperator, ingest_counts, plan_pca, prefetch_omega,
+from .._device import (DeviceCounts, HostCopy, ResidualOperator, ingest_counts, plan_pca, prefetch_omega,
                        randomized_pca)
 
 STATE_KEY = "geneclust_b200"
@@ -29,6 +29,7 @@ class HotPathState:
     fast_clusters: Optional[tuple] = None        # (labels int32, closeness float32, K) on the device, GeneClust-fast
     comm: object = None                          # optional GeneShardComm
     omega: object = None                         # OmegaPrefetch started by `start_omega`
+    host_copies: list = field(default_factory=list)   # HostCopy objects in flight (`finish_host_copies`)
     info: dict = field(default_factory=dict)
 
 
@@ -77,9 +78,21 @@ def normalize(adata, modality: Literal['sc', 'st'] = 'sc', materialize: bool = F
             adata.X = DeviceMatrix(st.Z) if isinstance(adata, AnnDataLite) else st.Z.cpu().numpy()
 
 
-def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):
+def finish_host_copies(adata):
+    """Wait for the host copies a stage left in flight (`reduce_dim(..., defer_host_copy=True)`)."""
+    st = get_state(adata)
+    for hc in st.host_copies:
+        hc.wait()
+    st.host_copies = []
+
+
+def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0, defer_host_copy: bool = False):
     """Gene-level PCA into `adata.varm['X_pca']` and, for GeneClust-ps, cell-level PCA into `adata.obsm['X_pca']`
-    (reference: pp/_preprocessing.py:35-55; sc.pp.pca -> sklearn PCA(50, svd_solver='auto') -> randomized SVD)."""
+    (reference: pp/_preprocessing.py:35-55; sc.pp.pca -> sklearn PCA(50, svd_solver='auto') -> randomized SVD).
+
+    `defer_host_copy=True` (the entry point): the ndarray put into `varm['X_pca']` is filled on a side stream while the
+    clustering already runs on the device copy; its contents are valid after `finish_host_copies(adata)`, which the
+    entry point calls before it returns.  The default waits for the copy, like any stage-by-stage caller expects."""
     st = get_state(adata)
     if st.op is None:
         raise RuntimeError("reduce_dim called before normalize")
@@ -89,7 +102,12 @@ def reduce_dim(adata, version: Literal['fast', 'ps'], random_state: int = 0):
     st.info['gene_pca'] = info
     if st.comm is not None:
         st.varm_pca = st.comm.all_gather_rows(st.varm_pca)
-    adata.varm['X_pca'] = st.varm_pca.cpu().numpy()
+    hc = HostCopy(st.varm_pca)
+    adata.varm['X_pca'] = hc.array
+    if defer_host_copy:
+        st.host_copies.append(hc)
+    else:
+        hc.wait()
     if version == 'ps':
         st.obsm_pca = randomized_pca(st.op, 'cells', random_state)
         adata.obsm['X_pca'] = st.obsm_pca.cpu().numpy()

@@ -25,6 +25,24 @@ def _pinned(name: str, n: int, dtype) -> torch.Tensor:
     return _PINNED[key]
 
 
+_CDF: dict = {}
+
+
+def _uniform_cdf(n: int, dev) -> torch.Tensor:
+    """The float64 cdf `RandomState.choice(n, size, p=ones(n, float32) / n)` searches (numpy mtrand.pyx: cumsum of p,
+    normalised by its last entry), on the device.  It depends on n only; kept for the process (160 KB at 20 000)."""
+    key = (int(n), str(dev))
+    if key not in _CDF:
+        p = np.ones(n, dtype=np.float32)
+        p = p / np.sum(p)
+        cdf = np.asarray(p, dtype=np.float64).cumsum()
+        cdf /= cdf[-1]
+        if len(_CDF) > 8:
+            _CDF.clear()
+        _CDF[key] = torch.from_numpy(cdf).to(dev)
+    return _CDF[key]
+
+
 class DeviceMiniBatchKMeans:
     """`sklearn.cluster.MiniBatchKMeans(n_clusters, batch_size, random_state, n_init='auto')` as the reference
     configures it (scGeneClust/tl/cluster.py:66-69), re-expressed for the device.
@@ -86,50 +104,49 @@ class DeviceMiniBatchKMeans:
         rs.randint(0, n, init_size)                          # validation set (only ranks inits; n_init == 1)
         centers = self._init_centroids(X, rs, init_size)
         centers_new = torch.empty_like(centers)
-        counts = torch.zeros(K, dtype=torch.float32, device=dev)
-        counts_h = np.zeros(K, dtype=np.float32)
 
         ewa, ewa_min, no_improvement, n_since_reassign = None, None, 0, 0
         n_steps = (self.max_iter * n) // batch
         # `random_state.choice(n, batch, p=sample_weight / sum)` (cluster/_kmeans.py:2169-2174) is, for replace=True
         # with p, `cdf.searchsorted(random_sample(batch), side='right')` with cdf = float64 cumsum of p normalised by
         # its last entry (numpy mtrand.pyx RandomState.choice); the cdf is the same every step, so it is built once
-        p = np.ones(n, dtype=np.float32)
-        p = p / np.sum(p)
-        cdf = np.asarray(p, dtype=np.float64).cumsum()
-        cdf /= cdf[-1]
+        cdf_dev = _uniform_cdf(n, dev)
         labels_b = torch.empty(batch, dtype=torch.int32, device=dev)
         sq_b = torch.empty(batch, dtype=torch.float32, device=dev)
-        inertia_d = torch.empty(1, dtype=torch.float64, device=dev)
         idx = torch.empty(batch, dtype=torch.int32, device=dev)
-        # pinned staging: per step one upload of the uniforms, one (two-part) read-back, one stream synchronisation and -
-        # when starved centres are reassigned - one upload of (cluster ids, picked batch positions)
+        # Host <-> device traffic of a step goes through pinned host buffers that the kernels address directly (unified
+        # addressing: a cudaHostAlloc'ed buffer has the same pointer on the device): the uniforms are read, the per-cluster
+        # counts and the batch inertia are kept, and the reassignment list is read there - no copy calls, one stream
+        # synchronisation per step (inherent: the next step's RandomState draws depend on this step's counts).
         u_pin = _pinned('u', batch, torch.float64)
-        u_dev = torch.empty(batch, dtype=torch.float64, device=dev)
-        cdf_dev = torch.from_numpy(cdf).to(dev)
-        counts_pin = _pinned('counts', K, torch.float32)
+        counts = _pinned('counts', K, torch.float32)
+        counts.zero_()
+        counts_h = np.zeros(K, dtype=np.float32)
+        counts_view = counts.numpy()
         inertia_pin = _pinned('inertia', 1, torch.float64)
+        inertia_view = inertia_pin.numpy()
         re_pin = _pinned('reassign', 2 * K, torch.int32)
-        re_dev = torch.empty(2 * K, dtype=torch.int32, device=dev)
+        re_np = re_pin.numpy()
+        u_np = u_pin.numpy()
         stream = torch.cuda.current_stream()
+        p_X, ldx, p_cdf, p_u, p_idx, p_lab, p_sq = ptr(X), X.stride(0), ptr(cdf_dev), ptr(u_pin), ptr(idx), ptr(labels_b), ptr(sq_b)
+        p_counts, p_inertia, p_re = ptr(counts), ptr(inertia_pin), ptr(re_pin)
+        p_c, p_cn = ptr(centers), ptr(centers_new)
         step = 0
         for step in range(n_steps):
-            # the uniform draws go up, the searchsorted runs on the device against the same float64 cdf
-            u_pin.numpy()[:] = rs.random_sample(batch)
-            u_dev.copy_(u_pin, non_blocking=True)
+            u_np[:] = rs.random_sample(batch)
             # _random_reassign(), evaluated before the step on the counts of the previous one
             n_since_reassign += batch
             random_reassign = bool((counts_h == 0).any() or n_since_reassign >= 10 * K)
             if random_reassign:
                 n_since_reassign = 0
-            # _mini_batch_step: one call enqueues batch selection, assignment, inertia and centre update
-            L.kmeans_minibatch_step(ptr(X), X.stride(0), n, d, K, ptr(cdf_dev), ptr(u_dev), batch, ptr(idx), ptr(labels_b),
-                                    ptr(sq_b), ptr(centers), ptr(centers_new), ptr(counts), ptr(inertia_d), st)
-            counts_pin.copy_(counts, non_blocking=True)
-            inertia_pin.copy_(inertia_d, non_blocking=True)
+            # _mini_batch_step: one call enqueues batch selection (searchsorted of the uniforms against the float64 cdf),
+            # assignment, inertia and centre update
+            L.kmeans_minibatch_step(p_X, ldx, n, d, K, p_cdf, p_u, batch, p_idx, p_lab, p_sq, p_c, p_cn, p_counts,
+                                    p_inertia, st)
             stream.synchronize()
-            counts_h = counts_pin.numpy().copy()
-            batch_inertia = float(np.float32(inertia_pin.numpy()[0]))
+            counts_h = counts_view.copy()
+            batch_inertia = float(np.float32(inertia_view[0]))
             if random_reassign and self.reassignment_ratio > 0:
                 to_reassign = counts_h < self.reassignment_ratio * counts_h.max()
                 if to_reassign.sum() > 0.5 * batch:
@@ -141,12 +158,11 @@ class DeviceMiniBatchKMeans:
                     # the "dirty hack" count reset of _mini_batch_step (cluster/_kmeans.py:1679-1682)
                     min_count = np.min(counts_h[~to_reassign])
                     counts_h[to_reassign] = min_count
-                    re_np = re_pin.numpy()
                     re_np[:n_reassigns] = np.flatnonzero(to_reassign)
                     re_np[K:K + n_reassigns] = picks
-                    re_dev.copy_(re_pin, non_blocking=True)
-                    L.kmeans_reassign(ptr(X), X.stride(0), d, ptr(idx), ptr(re_dev), ptr(re_dev[K:]), n_reassigns,
-                                      float(min_count), ptr(centers_new), ptr(counts), st)
+                    L.kmeans_reassign(p_X, ldx, d, p_idx, p_re, p_re + 4 * K, n_reassigns, float(min_count), p_cn,
+                                      p_counts, st)
+            p_c, p_cn = p_cn, p_c
             centers, centers_new = centers_new, centers
             # _mini_batch_convergence (tol == 0)
             batch_inertia /= batch
@@ -200,7 +216,12 @@ def cluster_genes(adata, img: Optional[np.ndarray], version: Literal['fast', 'ps
                                    random_state=random_state)
         labels = km.fit_predict(X)
         closeness = compute_gene_closeness(X, labels, km.cluster_centers_)
-        labels_h, closeness_h = labels.cpu().numpy(), closeness.cpu().numpy()
+        # one synchronisation for both read-backs (pinned staging; the var columns get their own arrays)
+        lab_pin, clo_pin = _pinned('labels', labels.numel(), torch.int32), _pinned('closeness', closeness.numel(), torch.float32)
+        lab_pin.copy_(labels, non_blocking=True)
+        clo_pin.copy_(closeness, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        labels_h, closeness_h = lab_pin.numpy().copy(), clo_pin.numpy().copy()
         adata.var['cluster'] = labels_h
         adata.var['closeness'] = closeness_h
         # the selection stage reduces these on the device as long as the var columns still hold these values
