@@ -208,6 +208,11 @@ int gc_cluster_extremes(const float *value, const int32_t *labels, int64_t n, in
  * scratch: gc_binomial_deviance_scratch_bytes(C, m), 256-byte aligned. */
 int64_t gc_binomial_deviance_scratch_bytes(int64_t C, int m);
 int gc_binomial_deviance(const float *X, int64_t C, int m, float *out, void *scratch, void *stream);
+/* The building block of the above, exposed for tests: out[j] = numpy's a.sum(0)[j] for a C-ordered float32 (C, m > 1)
+ * array, i.e. the sequential float32 chain a[0,j] + a[1,j] + ... (np.nansum at scGeneClust/tl/selection.py:86-87 after
+ * the NaN replacement), evaluated piece-parallel and bit-exact for m <= 64.  replays (m int32, or NULL): how many of the
+ * ceil(C / 256) pieces had to be replayed add by add.  scratch: gc_binomial_deviance_scratch_bytes(C, m). */
+int gc_sum_axis0_f32(const float *a, int64_t C, int m, float *out, int32_t *replays, void *scratch, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * a6/a7/a8  kNN mutual information (GeneClust-ps).  Replaces sklearn mutual_info_classif /

@@ -66,6 +66,7 @@ SIGNATURES = {
     "gc_closeness": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p]),
     "gc_binomial_deviance_scratch_bytes": (_i64, [_i64, C.c_int]),
     "gc_binomial_deviance": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p]),
+    "gc_sum_axis0_f32": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, _p]),
     "gc_mi_prepare": (C.c_int, [_p, _i64, _p, _p, C.c_int, _i64, _i64, _p, _p, _p, _p, _p]),
     "gc_mi_cc_pairs": (C.c_int, [_p, _p, _i64, C.c_int, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "gc_mi_cc_pairs_scratch_bytes": (_i64, [_i64, C.c_int]),

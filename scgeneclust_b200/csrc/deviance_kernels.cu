@@ -155,6 +155,173 @@ colsum_sequential_kernel(const float *__restrict__ a0, const float *__restrict__
     if (tid < mc) out[j0 + tid] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same sequential float32 column sums, piece-parallel and still bit-exact (m <= kSpecMaxCols).
+//
+// While the accumulator stays inside one binade [2^e, 2^(e+1)) (ulp u = 2^(e-23)) and keeps its sign,
+// fl(acc + x) = acc + sgn * rn_u(sgn * x) in integer arithmetic in units of u; only a tie (|x| / u has fraction exactly
+// 1/2) needs the parity of acc.  So a piece of kSpecPiece rows is summarised independently of what came before it as
+// two integer deltas (acc even / odd on entry) plus the extremes of the running offset, given a GUESS of (sign, e) -
+// taken from float64 prefix sums of the pieces.  One warp per column then walks the pieces: it checks the guess
+// against the true accumulator (same sign and exponent, the running offset never leaves the binade's interior) and
+// applies the delta, or replays the piece add by add when the check fails.  Exact by construction - the guess only
+// decides the speed: the deviance terms grow steadily (a dozen replays in 1500 pieces), a column sum that wanders
+// around zero replays most pieces and costs what the plain chain costs.  Prototype and adversarial test (ties, sign
+// changes, binade crossings): scripts/proto/spec_colsum.py.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSpecPiece = 256, kSpecMaxCols = 64;
+
+struct SpecSummary {
+    int32_t ok, sgn, e, pad;
+    int32_t d[2], mn[2], mx[2];
+};
+
+__device__ __forceinline__ const float *spec_array(const float *a0, const float *a1) { return blockIdx.y == 0 ? a0 : a1; }
+
+// sums[arr][p * m + j] = float64 sum of column j over piece p
+__global__ void __launch_bounds__(kSpecPiece)
+colsum_spec_sums_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m, int64_t n_pieces,
+                        double *__restrict__ sums) {
+    const float *__restrict__ a = spec_array(a0, a1);
+    __shared__ double warp_part[kSpecPiece / 32][kSpecMaxCols];
+    const int64_t row = (int64_t)blockIdx.x * kSpecPiece + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = 0; j < m; ++j) {
+        double v = row < C ? (double)a[row * m + j] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) warp_part[warp][j] = v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < m) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kSpecPiece / 32; ++w) t += warp_part[w][threadIdx.x];
+        sums[((int64_t)blockIdx.y * n_pieces + blockIdx.x) * m + threadIdx.x] = t;
+    }
+}
+
+// in place: sums -> exclusive prefix over the pieces (the float64 estimate of the accumulator on entry of a piece)
+__global__ void colsum_spec_prefix_kernel(double *__restrict__ sums, int m, int64_t n_pieces) {
+    const int j = threadIdx.x;
+    if (j >= m) return;
+    double *s = sums + (int64_t)blockIdx.y * n_pieces * m + j;
+    double run = 0.0;
+    for (int64_t p = 0; p < n_pieces; ++p) {
+        const double t = s[p * m];
+        s[p * m] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+colsum_spec_summary_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m, int64_t n_pieces,
+                           const double *__restrict__ est, SpecSummary *__restrict__ summ) {
+    const float *__restrict__ a = spec_array(a0, a1);
+    const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (idx >= n_pieces * m) return;
+    const int64_t p = idx / m;
+    const int j = (int)(idx - p * m);
+    const double g = est[(int64_t)blockIdx.y * n_pieces * m + idx];
+    SpecSummary out;
+    out.ok = 0; out.sgn = 0; out.e = 0; out.pad = 0;
+    out.d[0] = out.d[1] = out.mn[0] = out.mn[1] = out.mx[0] = out.mx[1] = 0;
+    bool ok = p > 0 && isfinite(g) && g != 0.0;
+    const int sgn = g > 0.0 ? 1 : -1;
+    const int e = ok ? ilogb(fabs(g)) : 0;
+    if (e < -100 || e > 100) ok = false;
+    long long d0 = 0, d1 = 0, mn0 = 0, mn1 = 0, mx0 = 0, mx1 = 0;
+    if (ok) {
+        const int64_t r_lo = p * kSpecPiece, r_hi = min(C, r_lo + kSpecPiece);
+        for (int64_t r = r_lo; r < r_hi; ++r) {
+            const uint32_t b = __float_as_uint(a[r * m + j]);
+            const int ex_raw = (b >> 23) & 0xff;
+            uint32_t M = b & 0x7fffffu;
+            if (ex_raw == 255) { ok = false; break; }                       // inf / nan: replay
+            int ex;
+            if (ex_raw == 0) ex = -149; else { M |= 0x800000u; ex = ex_raw - 150; }
+            if (M == 0) continue;
+            const int s = (b >> 31) ? -sgn : sgn;
+            const int sh = (e - 23) - ex;
+            long long inc0, inc1;
+            if (sh <= 0) {
+                if (sh < -2) { ok = false; break; }                          // |x| >= 4 |acc|: leaves the binade anyway
+                inc0 = inc1 = (long long)M << (-sh);
+            } else if (sh >= 25) {
+                continue;                                                    // |x| < u / 2
+            } else {
+                const uint32_t q = M >> sh, rem = M & ((1u << sh) - 1u), half = 1u << (sh - 1);
+                if (rem > half) {
+                    inc0 = inc1 = (long long)q + 1;
+                } else if (rem == half) {                                    // tie: to the even result
+                    inc0 = (long long)q + (((0 + d0 + s * (long long)q) & 1) ? 1 : 0);
+                    inc1 = (long long)q + (((1 + d1 + s * (long long)q) & 1) ? 1 : 0);
+                } else {
+                    inc0 = inc1 = q;
+                }
+            }
+            d0 += s * inc0; d1 += s * inc1;
+            mn0 = min(mn0, d0); mx0 = max(mx0, d0);
+            mn1 = min(mn1, d1); mx1 = max(mx1, d1);
+        }
+        const long long lim = 1LL << 28;
+        if (mn0 < -lim || mn1 < -lim || mx0 > lim || mx1 > lim) ok = false;
+    }
+    if (ok) {
+        out.ok = 1; out.sgn = sgn; out.e = e;
+        out.d[0] = (int32_t)d0; out.d[1] = (int32_t)d1;
+        out.mn[0] = (int32_t)mn0; out.mn[1] = (int32_t)mn1;
+        out.mx[0] = (int32_t)mx0; out.mx[1] = (int32_t)mx1;
+    }
+    summ[(int64_t)blockIdx.y * n_pieces * m + idx] = out;
+}
+
+// one warp per column: every lane carries the same accumulator; a replayed piece is loaded 32 rows at a time (one row
+// per lane, the next block before the adds of the current one) and handed to the chain by shuffles
+__global__ void __launch_bounds__(32)
+colsum_spec_chain_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m, int64_t n_pieces,
+                         const SpecSummary *__restrict__ summ, float *__restrict__ out0, float *__restrict__ out1,
+                         int32_t *__restrict__ replays) {
+    const float *__restrict__ a = spec_array(a0, a1);
+    float *__restrict__ out = blockIdx.y == 0 ? out0 : out1;
+    const int j = blockIdx.x, lane = threadIdx.x;
+    const SpecSummary *S = summ + (int64_t)blockIdx.y * n_pieces * m + j;
+    float acc = a[j];                                                        // the reduction starts from the first row
+    int n_replay = 0;
+    for (int64_t p = 0; p < n_pieces; ++p) {
+        const int64_t r_lo = p == 0 ? 1 : p * kSpecPiece, r_hi = min(C, (p + 1) * kSpecPiece);
+        const SpecSummary sm = S[p * m];
+        const uint32_t bits = __float_as_uint(acc);
+        const int ex = (bits >> 23) & 0xff;
+        bool fast = sm.ok && ex != 0 && ex != 255 && ((bits >> 31) ? -1 : 1) == sm.sgn && ex - 127 == sm.e;
+        if (fast) {
+            const int32_t ai = (int32_t)((bits & 0x7fffffu) | 0x800000u);
+            const int par = ai & 1;
+            fast = ai + sm.mn[par] >= (1 << 23) + 1 && ai + sm.mx[par] <= (1 << 24) - 2;
+            if (fast) acc = __uint_as_float((bits & 0xff800000u) | ((uint32_t)(ai + sm.d[par]) & 0x7fffffu));
+        }
+        if (!fast) {
+            ++n_replay;
+            float v = r_lo + lane < r_hi ? a[(r_lo + lane) * m + j] : 0.f;
+            for (int64_t r0 = r_lo; r0 < r_hi; r0 += 32) {
+                const float cur = v;
+                v = r0 + 32 + lane < r_hi ? a[(r0 + 32 + lane) * m + j] : 0.f;
+                const int cnt = (int)min((int64_t)32, r_hi - r0);
+                if (cnt == 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur, k));
+                } else {
+                    for (int k = 0; k < cnt; ++k) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur, k));
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        out[j] = acc;
+        if (replays) replays[blockIdx.y * m + j] = n_replay;
+    }
+}
+
 // per row: n_i = pairwise sum of the row; L[i,j], R[i,j] with NaN -> 0 (np.nansum's _replace_nan)
 __global__ void deviance_terms_kernel(const float *__restrict__ X, int64_t C, int m, const float *__restrict__ colsum,
                                       const float *__restrict__ total, float *__restrict__ L, float *__restrict__ R) {
@@ -186,8 +353,39 @@ using namespace gc;
 
 static int64_t dev_align(int64_t x) { return (x + 255) / 256 * 256; }
 
+static int64_t spec_pieces(int64_t C) { return (C + kSpecPiece - 1) / kSpecPiece; }
+static int64_t spec_bytes(int64_t C, int m) {
+    if (m > kSpecMaxCols) return 0;
+    return 2 * (dev_align(spec_pieces(C) * m * 8) + dev_align(spec_pieces(C) * m * (int64_t)sizeof(SpecSummary))) +
+           dev_align(2 * kSpecMaxCols * 4);
+}
+
 extern "C" int64_t gc_binomial_deviance_scratch_bytes(int64_t C, int m) {
-    return 2 * dev_align(C * m * 4) + dev_align(3 * (1 << kDevDepth) * 4) + 4 * dev_align((int64_t)m * 4 + 16) + 512;
+    return 2 * dev_align(C * m * 4) + dev_align(3 * (1 << kDevDepth) * 4) + 4 * dev_align((int64_t)m * 4 + 16) + 512 +
+           spec_bytes(C, m);
+}
+
+// out0[j] (and out1[j]) = sequential float32 sum of column j of a0 (a1): piece-parallel when m <= kSpecMaxCols
+static int colsum_axis0(const float *a0, const float *a1, int64_t C, int m, float *out0, float *out1, char *spec,
+                        cudaStream_t st) {
+    const unsigned n_arr = a1 ? 2 : 1;
+    if (m > kSpecMaxCols) {
+        const int cb = m <= kColThreads ? kColThreads : 64;      // columns per CTA of the sequential column sums
+        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, cb), n_arr), kColThreads, 0, st>>>(a0, a1, C, m, cb, out0, out1);
+        return check_launch("colsum_sequential_kernel");
+    }
+    const int64_t P = spec_pieces(C);
+    double *sums = (double *)spec;
+    SpecSummary *summ = (SpecSummary *)(spec + 2 * dev_align(P * m * 8));
+    int32_t *replays = (int32_t *)(spec + 2 * dev_align(P * m * 8) + 2 * dev_align(P * m * (int64_t)sizeof(SpecSummary)));
+    colsum_spec_sums_kernel<<<dim3((unsigned)P, n_arr), kSpecPiece, 0, st>>>(a0, a1, C, m, P, sums);
+    if (int rc = check_launch("colsum_spec_sums_kernel")) return rc;
+    colsum_spec_prefix_kernel<<<dim3(1, n_arr), kSpecMaxCols, 0, st>>>(sums, m, P);
+    if (int rc = check_launch("colsum_spec_prefix_kernel")) return rc;
+    colsum_spec_summary_kernel<<<dim3((unsigned)ceil_div<int64_t>(P * m, 128), n_arr), 128, 0, st>>>(a0, a1, C, m, P, sums, summ);
+    if (int rc = check_launch("colsum_spec_summary_kernel")) return rc;
+    colsum_spec_chain_kernel<<<dim3((unsigned)m, n_arr), 32, 0, st>>>(a0, a1, C, m, P, summ, out0, out1, replays);
+    return check_launch("colsum_spec_chain_kernel");
 }
 
 extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out, void *scratch, void *stream) {
@@ -202,9 +400,9 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
     float *colsum = (float *)p;    p += dev_align((int64_t)m * 4 + 16);
     float *total = (float *)p;     p += dev_align((int64_t)m * 4 + 16);
     float *left = (float *)p;      p += dev_align((int64_t)m * 4 + 16);
-    float *right = (float *)p;
+    float *right = (float *)p;     p += dev_align((int64_t)m * 4 + 16) + 256;
+    char *spec = p;
     const int64_t n_all = C * (int64_t)m;
-    const int cb = m <= kColThreads ? kColThreads : 64;      // columns per CTA of the sequential column sums
     const int depth = pairwise_depth(n_all);
     const int n_sub = 1 << depth;
     // X.sum() (and, for m == 1, the column sum is the same number)
@@ -215,8 +413,7 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
     if (m == 1) {
         GC_CUDA(cudaMemcpyAsync(colsum, total, sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, cb), 1), kColThreads, 0, st>>>(X, nullptr, C, m, cb, colsum, nullptr);
-        if (int rc = check_launch("colsum_sequential_kernel")) return rc;
+        if (int rc = colsum_axis0(X, nullptr, C, m, colsum, nullptr, spec, st)) return rc;
     }
     deviance_terms_kernel<<<(unsigned)ceil_div<int64_t>(C, 128), 128, 0, st>>>(X, C, m, colsum, total, L, R);
     if (int rc = check_launch("deviance_terms_kernel")) return rc;
@@ -228,9 +425,23 @@ extern "C" int gc_binomial_deviance(const float *X, int64_t C, int m, float *out
         // the second block wrote left[1]; move it to right[0]
         GC_CUDA(cudaMemcpyAsync(right, left + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-        colsum_sequential_kernel<<<dim3((unsigned)ceil_div(m, cb), 2), kColThreads, 0, st>>>(L, R, C, m, cb, left, right);
-        if (int rc = check_launch("colsum_sequential_kernel")) return rc;
+        if (int rc = colsum_axis0(L, R, C, m, left, right, spec, st)) return rc;
     }
     deviance_finish_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, st>>>(left, right, m, out);
     return check_launch("deviance_finish_kernel");
+}
+
+extern "C" int gc_sum_axis0_f32(const float *a, int64_t C, int m, float *out, int32_t *replays, void *scratch, void *stream) {
+    GC_REQUIRE(a && out && scratch, "null pointer");
+    GC_REQUIRE(C >= 1 && m >= 2, "bad shape (m == 1 is numpy's pairwise sum: gc_binomial_deviance handles it)");
+    GC_REQUIRE(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    char *spec = (char *)scratch;
+    if (int rc = colsum_axis0(a, nullptr, C, m, out, nullptr, spec, st)) return rc;
+    if (replays && m <= kSpecMaxCols) {
+        const int64_t P = spec_pieces(C);
+        const int32_t *src = (const int32_t *)(spec + 2 * dev_align(P * m * 8) + 2 * dev_align(P * m * (int64_t)sizeof(SpecSummary)));
+        GC_CUDA(cudaMemcpyAsync(replays, src, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
 }

@@ -418,16 +418,27 @@ panel_gram_partial_kernel(const float *__restrict__ P, int64_t rows, int64_t row
         for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * kQ + tx * 4 + j] = acc[i][j];
 }
 
-// fixed summation order over the partials; entries of a block below the diagonal are read from the mirrored block
-__global__ void panel_gram_reduce_kernel(const double *__restrict__ partial, int n_part, double *__restrict__ Gm) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kQ * kQ) return;
+// Fixed summation order over the partials: eight contiguous ranges of them are summed by eight threads per entry and
+// combined in range order.  Entries of a block below the diagonal are read from the mirrored block.
+__global__ void __launch_bounds__(256)
+panel_gram_reduce_kernel(const double *__restrict__ partial, int n_part, double *__restrict__ Gm) {
+    __shared__ double seg_sum[8][32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;                       // 128 CTAs x 32 entries
     const int r = i / kQ, c = i % kQ;
     const int src = (r >> 2) <= (c >> 2) ? i : c * kQ + r;
+    const int per = (n_part + 7) / 8, p_lo = seg * per, p_hi = min(n_part, p_lo + per);
     double s = 0.0;
-#pragma unroll 8
-    for (int p = 0; p < n_part; ++p) s += partial[(int64_t)p * kQ * kQ + src];
-    Gm[i] = s;
+#pragma unroll 4
+    for (int p = p_lo; p < p_hi; ++p) s += partial[(int64_t)p * kQ * kQ + src];
+    seg_sum[seg][lane] = s;
+    __syncthreads();
+    if (seg == 0) {
+        double t = seg_sum[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += seg_sum[k][lane];
+        Gm[i] = t;
+    }
 }
 
 // Pout = P @ R ; optional column-wise |.|-max candidates (first index on ties) per CTA
@@ -739,7 +750,7 @@ extern "C" int gc_panel_gram(const float *P, int64_t rows, double *Gm, void *scr
     const int n_part = (int)ceil_div<int64_t>(rows, per);
     panel_gram_partial_kernel<<<n_part, kGramThreads, 0, as_stream(stream)>>>(P, rows, per, (double *)scratch);
     if (int rc = check_launch("panel_gram_partial_kernel")) return rc;
-    panel_gram_reduce_kernel<<<kQ * kQ / 256, 256, 0, as_stream(stream)>>>((const double *)scratch, n_part, Gm);
+    panel_gram_reduce_kernel<<<kQ * kQ / 32, 256, 0, as_stream(stream)>>>((const double *)scratch, n_part, Gm);
     return check_launch("panel_gram_reduce_kernel");
 }
 

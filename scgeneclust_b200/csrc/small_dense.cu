@@ -35,21 +35,28 @@ chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, 
         X[i][c] = i == c ? 1.0 : 0.0;
     }
     __syncthreads();
+    // 1 / sqrt(pivot) is formed by ONE thread - the owner of the next pivot, right after it has updated it - while the
+    // others finish their updates of the step (a float64 rsqrt in all 1024 threads made the FP64 pipe the bottleneck)
+    auto pivot_rsqrt = [&](double piv, int j) {
+        if (!(piv > 0.0)) { atomicOr(status, 1); piv = 1.0; }
+        rdiag[j] = rsqrt(piv);
+    };
+    if (threadIdx.x == 0) pivot_rsqrt(A[0][0], 0);
+    __syncthreads();
     for (int j = 0; j < q; ++j) {
-        double piv = A[j][j];
-        if (!(piv > 0.0)) {
-            if (threadIdx.x == 0) atomicOr(status, 1);
-            piv = 1.0;
-        }
-        const double rs = rsqrt(piv);
-        if (threadIdx.x == 0) rdiag[j] = rs;
+        const double rs = rdiag[j];
         if (i > j && i < q) {
             const double w = -(A[i][j] * (rs * rs));
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int c = l + 16 * m;
-                if (c <= j) X[i][c] = fma(w, X[j][c], X[i][c]);
-                else if (c <= i) A[i][c] = fma(w, A[c][j], A[i][c]);
+                if (c <= j) {
+                    X[i][c] = fma(w, X[j][c], X[i][c]);
+                } else if (c <= i) {
+                    const double v = fma(w, A[c][j], A[i][c]);
+                    A[i][c] = v;
+                    if (i == j + 1 && c == i) pivot_rsqrt(v, i);
+                }
             }
         }
         __syncthreads();

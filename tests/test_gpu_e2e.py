@@ -287,3 +287,41 @@ def test_config_c2_true_shape_ps(torch_cuda, pbmc3k_substitute):
     edges = info.uns['mst_edges']
     pick = rs.choice(len(edges), 6, replace=False)
     assert np.array_equal(info.uns['mst_edges_complm'][pick], stages.gene_complementarity(Z, labels, edges[pick], 0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,m,kind", [(70001, 7, "walk"), (70001, 3, "grow"), (20000, 5, "ties"), (5000, 64, "mixed"),
+                                      (300, 2, "grow"), (400003, 7, "deviance"), (9000, 80, "walk")])
+def test_sum_axis0_is_numpy_sequential_sum(torch_cuda, C, m, kind):
+    """The piece-parallel column sum must return the bits of numpy's row-after-row float32 reduction, whatever the
+    data does to the speculation (sign changes, binade crossings, exact ties, huge entries, inf)."""
+    torch = torch_cuda
+    from scgeneclust_b200._lib import lib, ptr, stream_handle
+    rs = np.random.RandomState(C + m)
+    if kind == "walk":                                   # wanders around zero: most pieces are replayed
+        X = rs.standard_normal((C, m)).astype(np.float32)
+    elif kind == "grow":
+        X = np.abs(rs.standard_normal((C, m))).astype(np.float32) * 3
+    elif kind == "ties":                                 # multiples of half an ulp of sums near 2^20, 2^12 and 1
+        X = (rs.randint(-3, 4, (C, m)) * np.array([2.0 ** -4, 2.0 ** -12, 2.0 ** -24, 2.0 ** -4, 2.0 ** -13])).astype(np.float32)
+        X[0] = [2 ** 20, -2 ** 12 - 1, 1.0, -2 ** 20 + 0.5, 2 ** 11]
+    elif kind == "mixed":
+        X = (rs.standard_normal((C, m)) * np.exp(rs.uniform(-12, 12, (C, m)))).astype(np.float32)
+        X[rs.randint(C, size=3), rs.randint(m, size=3)] = [np.inf, 3e38, -3e38]
+    else:                                                # deviance-like terms: mostly positive, many zeros
+        v = rs.poisson(1.5, (C, m)).astype(np.float32)
+        with np.errstate(all="ignore"):
+            X = np.nan_to_num(v * np.log(v / 1.7), nan=0.0).astype(np.float32) - np.float32(0.05) * (v == 1)
+    with np.errstate(all="ignore"):
+        ref = X.sum(0)
+    L, st = lib(), stream_handle()
+    dX = torch.from_numpy(X).cuda()
+    out = torch.empty(m, dtype=torch.float32, device="cuda")
+    rep = torch.zeros(m, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(L.binomial_deviance_scratch_bytes(C, m) + 256, dtype=torch.uint8, device="cuda")
+    L.sum_axis0_f32(ptr(dX), C, m, ptr(out), ptr(rep), ptr(scratch), st)
+    got = out.cpu().numpy()
+    print(f"sum_axis0 {kind} C={C} m={m}: replayed pieces {rep.cpu().numpy().tolist()[:8]} of {-(-C // 256)}")
+    nan = np.isnan(ref)                                  # (x86 and CUDA encode an invalid-operation NaN differently)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got.view(np.uint32)[~nan], ref.view(np.uint32)[~nan]), (got, ref)

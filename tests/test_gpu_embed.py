@@ -179,7 +179,8 @@ def test_gene_pca_untransposed_shape(torch_cuda, small_counts):
     assert rel.max() <= 1e-3
 
 
-@pytest.mark.parametrize("seed,rows,q", [(0, 20000, 60), (7, 1237, 60), (123456, 50, 13), (2 ** 32 - 1, 3000, 60)])
+@pytest.mark.parametrize("seed,rows,q", [(0, 20000, 60), (7, 1237, 60), (123456, 50, 13), (2 ** 32 - 1, 3000, 60),
+                                         (5, 50000, 60)])
 def test_device_omega_equals_numpy_randomstate(torch_cuda, seed, rows, q):
     """The randomized solver's test matrix (sklearn utils/extmath.py:323-334) generated on the device from the seeded
     MT19937 state must be the float32 cast of numpy's own legacy stream: identical entries, zero padding columns."""
