@@ -201,13 +201,24 @@ colsum_spec_sums_kernel(const float *__restrict__ a0, const float *__restrict__ 
     }
 }
 
-// in place: sums -> exclusive prefix over the pieces (the float64 estimate of the accumulator on entry of a piece)
-__global__ void colsum_spec_prefix_kernel(double *__restrict__ sums, int m, int64_t n_pieces) {
-    const int j = threadIdx.x;
-    if (j >= m) return;
+// in place: sums -> exclusive prefix over the pieces (the float64 estimate of the accumulator on entry of a piece).
+// One warp per column: every lane scans a contiguous range of pieces, the range totals are scanned by shuffles.
+__global__ void __launch_bounds__(32)
+colsum_spec_prefix_kernel(double *__restrict__ sums, int m, int64_t n_pieces) {
+    const int j = blockIdx.x, lane = threadIdx.x;
     double *s = sums + (int64_t)blockIdx.y * n_pieces * m + j;
-    double run = 0.0;
-    for (int64_t p = 0; p < n_pieces; ++p) {
+    const int64_t per = (n_pieces + 31) / 32, p_lo = min(n_pieces, lane * per), p_hi = min(n_pieces, p_lo + per);
+    double tot = 0.0;
+#pragma unroll 4
+    for (int64_t p = p_lo; p < p_hi; ++p) tot += s[p * m];
+    double incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    double run = incl - tot;
+    for (int64_t p = p_lo; p < p_hi; ++p) {
         const double t = s[p * m];
         s[p * m] = run;
         run += t;
@@ -276,8 +287,10 @@ colsum_spec_summary_kernel(const float *__restrict__ a0, const float *__restrict
     summ[(int64_t)blockIdx.y * n_pieces * m + idx] = out;
 }
 
-// one warp per column: every lane carries the same accumulator; a replayed piece is loaded 32 rows at a time (one row
-// per lane, the next block before the adds of the current one) and handed to the chain by shuffles
+// One warp per column; every lane carries the same accumulator.  The summaries are fetched 32 pieces at a time (one
+// per lane) and handed round by shuffles.  A replayed piece is eight blocks of 32 rows, one row per lane and block,
+// all loaded before the first add (and already during the previous piece when the summary says the piece cannot be
+// taken in one step), handed to the chain by shuffles: four cycles per row, the FADD latency.
 __global__ void __launch_bounds__(32)
 colsum_spec_chain_kernel(const float *__restrict__ a0, const float *__restrict__ a1, int64_t C, int m, int64_t n_pieces,
                          const SpecSummary *__restrict__ summ, float *__restrict__ out0, float *__restrict__ out1,
@@ -286,32 +299,71 @@ colsum_spec_chain_kernel(const float *__restrict__ a0, const float *__restrict__
     float *__restrict__ out = blockIdx.y == 0 ? out0 : out1;
     const int j = blockIdx.x, lane = threadIdx.x;
     const SpecSummary *S = summ + (int64_t)blockIdx.y * n_pieces * m + j;
+    constexpr int kBlocks = kSpecPiece / 32;
     float acc = a[j];                                                        // the reduction starts from the first row
     int n_replay = 0;
-    for (int64_t p = 0; p < n_pieces; ++p) {
-        const int64_t r_lo = p == 0 ? 1 : p * kSpecPiece, r_hi = min(C, (p + 1) * kSpecPiece);
-        const SpecSummary sm = S[p * m];
-        const uint32_t bits = __float_as_uint(acc);
-        const int ex = (bits >> 23) & 0xff;
-        bool fast = sm.ok && ex != 0 && ex != 255 && ((bits >> 31) ? -1 : 1) == sm.sgn && ex - 127 == sm.e;
-        if (fast) {
-            const int32_t ai = (int32_t)((bits & 0x7fffffu) | 0x800000u);
-            const int par = ai & 1;
-            fast = ai + sm.mn[par] >= (1 << 23) + 1 && ai + sm.mx[par] <= (1 << 24) - 2;
-            if (fast) acc = __uint_as_float((bits & 0xff800000u) | ((uint32_t)(ai + sm.d[par]) & 0x7fffffu));
-        }
-        if (!fast) {
-            ++n_replay;
-            float v = r_lo + lane < r_hi ? a[(r_lo + lane) * m + j] : 0.f;
-            for (int64_t r0 = r_lo; r0 < r_hi; r0 += 32) {
-                const float cur = v;
-                v = r0 + 32 + lane < r_hi ? a[(r0 + 32 + lane) * m + j] : 0.f;
-                const int cnt = (int)min((int64_t)32, r_hi - r0);
-                if (cnt == 32) {
+    float nxt[kBlocks];
+    bool have_nxt = false;
+    auto load_piece = [&](int64_t p, float (&v)[kBlocks]) {
+        const int64_t r_lo = p * kSpecPiece;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur, k));
-                } else {
-                    for (int k = 0; k < cnt; ++k) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur, k));
+        for (int b = 0; b < kBlocks; ++b) {
+            const int64_t r = r_lo + b * 32 + lane;
+            v[b] = r < C ? a[r * m + j] : 0.f;
+        }
+    };
+    for (int64_t p0 = 0; p0 < n_pieces; p0 += 32) {
+        SpecSummary mine;
+        mine.ok = 0;
+        if (p0 + lane < n_pieces) mine = S[(p0 + lane) * m];
+        const int n_here = (int)min((int64_t)32, n_pieces - p0);
+        for (int k = 0; k < n_here; ++k) {
+            const int64_t p = p0 + k;
+            const int ok = __shfl_sync(0xffffffffu, mine.ok, k);
+            // rows of the NEXT piece, when it is known to need a replay (same batch only: its summary is at hand)
+            float cur[kBlocks];
+            const bool have_cur = have_nxt;
+            if (have_cur) {
+#pragma unroll
+                for (int b = 0; b < kBlocks; ++b) cur[b] = nxt[b];
+            }
+            have_nxt = false;
+            if (k + 1 < n_here && __shfl_sync(0xffffffffu, mine.ok, k + 1) == 0) {
+                load_piece(p + 1, nxt);
+                have_nxt = true;
+            }
+            bool fast = false;
+            if (ok) {
+                const int sgn = __shfl_sync(0xffffffffu, mine.sgn, k), e = __shfl_sync(0xffffffffu, mine.e, k);
+                const uint32_t bits = __float_as_uint(acc);
+                const int ex = (bits >> 23) & 0xff;
+                if (ex != 0 && ex != 255 && ((bits >> 31) ? -1 : 1) == sgn && ex - 127 == e) {
+                    const int32_t ai = (int32_t)((bits & 0x7fffffu) | 0x800000u);
+                    const int par = ai & 1;
+                    const int32_t d = __shfl_sync(0xffffffffu, par ? mine.d[1] : mine.d[0], k);
+                    const int32_t mn = __shfl_sync(0xffffffffu, par ? mine.mn[1] : mine.mn[0], k);
+                    const int32_t mx = __shfl_sync(0xffffffffu, par ? mine.mx[1] : mine.mx[0], k);
+                    if (ai + mn >= (1 << 23) + 1 && ai + mx <= (1 << 24) - 2) {
+                        acc = __uint_as_float((bits & 0xff800000u) | ((uint32_t)(ai + d) & 0x7fffffu));
+                        fast = true;
+                    }
+                }
+            }
+            if (!fast) {
+                ++n_replay;
+                if (!have_cur) load_piece(p, cur);
+                const int64_t r_lo = p * kSpecPiece, r_hi = min(C, r_lo + kSpecPiece);
+#pragma unroll
+                for (int b = 0; b < kBlocks; ++b) {
+                    const int64_t r0 = r_lo + b * 32;
+                    const int first = (p == 0 && b == 0) ? 1 : 0;              // row 0 started the accumulator
+                    const int cnt = (int)max((int64_t)0, min((int64_t)32, r_hi - r0));
+                    if (cnt == 32 && first == 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur[b], q));
+                    } else {
+                        for (int q = first; q < cnt; ++q) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur[b], q));
+                    }
                 }
             }
         }
@@ -380,7 +432,7 @@ static int colsum_axis0(const float *a0, const float *a1, int64_t C, int m, floa
     int32_t *replays = (int32_t *)(spec + 2 * dev_align(P * m * 8) + 2 * dev_align(P * m * (int64_t)sizeof(SpecSummary)));
     colsum_spec_sums_kernel<<<dim3((unsigned)P, n_arr), kSpecPiece, 0, st>>>(a0, a1, C, m, P, sums);
     if (int rc = check_launch("colsum_spec_sums_kernel")) return rc;
-    colsum_spec_prefix_kernel<<<dim3(1, n_arr), kSpecMaxCols, 0, st>>>(sums, m, P);
+    colsum_spec_prefix_kernel<<<dim3((unsigned)m, n_arr), 32, 0, st>>>(sums, m, P);
     if (int rc = check_launch("colsum_spec_prefix_kernel")) return rc;
     colsum_spec_summary_kernel<<<dim3((unsigned)ceil_div<int64_t>(P * m, 128), n_arr), 128, 0, st>>>(a0, a1, C, m, P, sums, summ);
     if (int rc = check_launch("colsum_spec_summary_kernel")) return rc;

@@ -76,21 +76,29 @@ count_sums_kernel(const uint16_t *__restrict__ counts, int64_t C, int64_t G, int
     unsigned int mx01 = 0, mx23 = 0, mx45 = 0, mx67 = 0;       // per-gene maxima, two uint16 lanes per word (__vmaxu2)
     const bool active = g0 < ld;  // ld is a multiple of 8, padded columns hold zeros
     const int rows = (int)min((int64_t)kSumRows, C - r0);
-    for (int r = 0; r < rows; ++r) {
-        unsigned int rs = 0;
-        if (active) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(counts + (r0 + r) * ld + g0);
-            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
-            mx01 = __vmaxu2(mx01, v.x); mx23 = __vmaxu2(mx23, v.y); mx45 = __vmaxu2(mx45, v.z); mx67 = __vmaxu2(mx67, v.w);
+    // four rows per iteration (four 16-byte loads in flight per thread); the row sums of a warp are folded by the
+    // hardware warp reduction (REDUX) instead of five shuffle steps per row
+    for (int rb = 0; rb < rows; rb += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (active && rb + u < rows) v[u] = *reinterpret_cast<const uint4 *>(counts + (r0 + rb + u) * ld + g0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned int w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            mx01 = __vmaxu2(mx01, v[u].x); mx23 = __vmaxu2(mx23, v[u].y);
+            mx45 = __vmaxu2(mx45, v[u].z); mx67 = __vmaxu2(mx67, v[u].w);
+            unsigned int rs = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const unsigned int lo = w[k] & 0xffffu, hi = w[k] >> 16;
                 cs[2 * k] += lo; cs[2 * k + 1] += hi; rs += lo + hi;
             }
+            rs = __reduce_add_sync(0xffffffffu, rs);
+            if ((threadIdx.x & 31) == 0 && rs) atomicAdd(&srow[rb + u], rs);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-        if ((threadIdx.x & 31) == 0 && rs) atomicAdd(&srow[r], rs);
     }
     __syncthreads();
     if (threadIdx.x < rows && srow[threadIdx.x]) atomicAdd(&row_sum[r0 + threadIdx.x], (unsigned long long)srow[threadIdx.x]);

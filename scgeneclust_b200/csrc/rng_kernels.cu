@@ -115,13 +115,17 @@ mt19937_jump_kernel(const uint32_t *__restrict__ y, uint32_t *__restrict__ prev)
     __shared__ uint32_t part[64][16];
     const int wi = threadIdx.x & 15, chunk = threadIdx.x >> 4;
     const int w = blockIdx.x * 16 + wi;                          // 39 CTAs x 16 words
-    constexpr int kDeg = 19937, kPer = (kDeg + 63) / 64;
-    const int i_lo = chunk * kPer, i_hi = min(kDeg, i_lo + kPer);
+    // 624 polynomial words over 64 chunks: ten words (320 coefficients) per thread, the last chunk takes what is left;
+    // the 32 loads of a word are independent (masked, not predicated), so they are all in flight together
+    constexpr int kWordsPer = 10;
+    const int pw_lo = chunk * kWordsPer, pw_hi = min(kMtN, pw_lo + kWordsPer);
     uint32_t acc = 0;
     if (w < kMtN) {
-        for (int i = i_lo; i < i_hi; ++i) {
-            const uint32_t bit = (kMtJumpPoly[i >> 5] >> (i & 31)) & 1u;
-            acc ^= y[i + w] & (0u - bit);
+        for (int pw = pw_lo; pw < pw_hi; ++pw) {
+            const uint32_t g = kMtJumpPoly[pw];                    // coefficients 32 pw .. 32 pw + 31 (zero above 19936)
+            const uint32_t *yy = y + 32 * pw + w;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) acc ^= yy[b] & (0u - ((g >> b) & 1u));
         }
     }
     part[chunk][wi] = acc;
