@@ -69,8 +69,8 @@ count_sums_kernel(const uint16_t *__restrict__ counts, int64_t C, int64_t G, int
                   uint32_t *__restrict__ col_max) {
     __shared__ unsigned int srow[kSumRows];
     const int64_t r0 = (int64_t)blockIdx.y * kSumRows;
-    const int64_t g0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
-    if (threadIdx.x < kSumRows) srow[threadIdx.x] = 0;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;      // blockDim.x = 64 .. 256, see the launch
+    for (int r = threadIdx.x; r < kSumRows; r += blockDim.x) srow[r] = 0;
     __syncthreads();
     unsigned int cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned int mx01 = 0, mx23 = 0, mx45 = 0, mx67 = 0;       // per-gene maxima, two uint16 lanes per word (__vmaxu2)
@@ -101,7 +101,8 @@ count_sums_kernel(const uint16_t *__restrict__ counts, int64_t C, int64_t G, int
         }
     }
     __syncthreads();
-    if (threadIdx.x < rows && srow[threadIdx.x]) atomicAdd(&row_sum[r0 + threadIdx.x], (unsigned long long)srow[threadIdx.x]);
+    for (int r = threadIdx.x; r < rows; r += blockDim.x)
+        if (srow[r]) atomicAdd(&row_sum[r0 + r], (unsigned long long)srow[r]);
     if (active) {
         const unsigned int mx[8] = {mx01 & 0xffffu, mx01 >> 16, mx23 & 0xffffu, mx23 >> 16,
                                     mx45 & 0xffffu, mx45 >> 16, mx67 & 0xffffu, mx67 >> 16};
@@ -512,15 +513,33 @@ panel_matmul_kernel(const float *__restrict__ P, int64_t rows, const float *__re
     }
 }
 
-__global__ void colabsmax_reduce_kernel(const float *__restrict__ cand_val, int64_t n_cta, float *__restrict__ out_val) {
-    const int j = threadIdx.x;
-    if (j >= kQ) return;
-    float best = 0.f; bool have = false;
-    for (int64_t b = 0; b < n_cta; ++b) {      // ascending row blocks => first index wins ties
+// one CTA per column; (|value| larger, else block index smaller) is associative, so the tree keeps the first-index rule
+__global__ void __launch_bounds__(256)
+colabsmax_reduce_kernel(const float *__restrict__ cand_val, int64_t n_cta, float *__restrict__ out_val) {
+    __shared__ float s_val[256];
+    __shared__ long long s_blk[256];
+    const int j = blockIdx.x;
+    float best = 0.f;
+    long long best_b = -1;
+    for (int64_t b = threadIdx.x; b < n_cta; b += 256) {       // ascending row blocks within a thread
         const float v = cand_val[b * kQ + j];
-        if (!have || fabsf(v) > fabsf(best)) { best = v; have = true; }
+        if (best_b < 0 || fabsf(v) > fabsf(best)) { best = v; best_b = b; }
     }
-    out_val[j] = best;
+    s_val[threadIdx.x] = best; s_blk[threadIdx.x] = best_b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const float v = s_val[threadIdx.x + o];
+            const long long vb = s_blk[threadIdx.x + o];
+            const float cur = s_val[threadIdx.x];
+            const long long cb = s_blk[threadIdx.x];
+            if (vb >= 0 && (cb < 0 || fabsf(v) > fabsf(cur) || (fabsf(v) == fabsf(cur) && vb < cb))) {
+                s_val[threadIdx.x] = v; s_blk[threadIdx.x] = vb;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_val[j] = s_val[0];
 }
 
 }  // namespace gc
@@ -635,8 +654,16 @@ extern "C" int gc_count_sums(const uint16_t *counts, int64_t C, int64_t G, int64
                              unsigned long long *col_sum, uint32_t *col_max, void *stream) {
     if (int rc = check_counts_layout(counts, C, G, ld)) return rc;
     GC_REQUIRE(row_sum && col_sum, "null pointer");
-    dim3 grid((unsigned)ceil_div<int64_t>(ld, 2048), (unsigned)ceil_div<int64_t>(C, kSumRows));
-    count_sums_kernel<<<grid, 256, 0, as_stream(stream)>>>(counts, C, G, ld, row_sum, col_sum, col_max);
+    // CTA width (8 columns per thread) with the least padding of the last column tile: a 2 560-column gene shard is five
+    // 512-column tiles, not two 2 048-column ones
+    int threads = 256;
+    int64_t best_pad = -1;
+    for (int t = 256; t >= 64; t -= 64) {
+        const int64_t pad = ceil_div<int64_t>(ld, t * 8) * t * 8 - ld;
+        if (best_pad < 0 || pad < best_pad) { best_pad = pad; threads = t; }
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(ld, threads * 8), (unsigned)ceil_div<int64_t>(C, kSumRows));
+    count_sums_kernel<<<grid, threads, 0, as_stream(stream)>>>(counts, C, G, ld, row_sum, col_sum, col_max);
     return check_launch("count_sums_kernel");
 }
 
@@ -777,6 +804,6 @@ extern "C" int gc_panel_colabsmax(const float *P, int64_t rows, const float *R, 
     long long *cand_idx = (long long *)((char *)scratch + ((n_cta * kQ * 4 + 255) / 256) * 256);
     panel_matmul_kernel<true><<<(unsigned)n_cta, 256, 0, as_stream(stream)>>>(P, rows, R, nullptr, cand_val, cand_idx);
     if (int rc = check_launch("panel_matmul_kernel<absmax>")) return rc;
-    colabsmax_reduce_kernel<<<1, kQ, 0, as_stream(stream)>>>(cand_val, n_cta, out_val);
+    colabsmax_reduce_kernel<<<kQ, 256, 0, as_stream(stream)>>>(cand_val, n_cta, out_val);
     return check_launch("colabsmax_reduce_kernel");
 }
