@@ -9,6 +9,18 @@ namespace gc {
 
 constexpr int kN = 64;
 
+// 1 / sqrt(x) to ~2e-16 relative for x > 0: float32 seed (2^-22) and two Newton steps in float64 - a third of the
+// latency of rsqrt(double), which sits on the serial path of every Cholesky column and every Jacobi round
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const float xf = (float)x;
+    if (!(xf > 1e-30f && xf < 1e30f)) return rsqrt(x);
+    double y = (double)rsqrtf(xf);
+    const double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
+
 // Cholesky Gm = L L^T of the leading q x q block, then Rinv = (L^-1)^T as float32 (64 x 64, zero padded), so that
 // P @ Rinv has orthonormal columns when Gm = P^T P.  status[0] |= 1 on a non-positive pivot.
 //
@@ -39,7 +51,7 @@ chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, 
     // others finish their updates of the step (a float64 rsqrt in all 1024 threads made the FP64 pipe the bottleneck)
     auto pivot_rsqrt = [&](double piv, int j) {
         if (!(piv > 0.0)) { atomicOr(status, 1); piv = 1.0; }
-        rdiag[j] = rsqrt(piv);
+        rdiag[j] = fast_rsqrt(piv);
     };
     if (threadIdx.x == 0) pivot_rsqrt(A[0][0], 0);
     __syncthreads();
@@ -47,16 +59,19 @@ chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, 
         const double rs = rdiag[j];
         if (i > j && i < q) {
             const double w = -(A[i][j] * (rs * rs));
+            // the owner of the next pivot updates it first and forms its reciprocal square root - the one long
+            // dependent chain of the step - before its other entries
+            const bool owns_pivot = i == j + 1 && l == (i & 15);
+            if (owns_pivot) {
+                const double v = fma(w, A[i][j], A[i][i]);
+                A[i][i] = v;
+                pivot_rsqrt(v, i);
+            }
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int c = l + 16 * m;
-                if (c <= j) {
-                    X[i][c] = fma(w, X[j][c], X[i][c]);
-                } else if (c <= i) {
-                    const double v = fma(w, A[c][j], A[i][c]);
-                    A[i][c] = v;
-                    if (i == j + 1 && c == i) pivot_rsqrt(v, i);
-                }
+                if (c <= j) X[i][c] = fma(w, X[j][c], X[i][c]);
+                else if (c <= i && !(owns_pivot && c == i)) A[i][c] = fma(w, A[c][j], A[i][c]);
             }
         }
         __syncthreads();
@@ -125,18 +140,20 @@ sym_eig_kernel(const double *__restrict__ Gm, int q, double *__restrict__ evals,
         for (int round = 0; round < m - 1; ++round) {
             if (tid < n_pairs) {
                 // round-robin tournament: player m-1 fixed, the others rotate
-                int a = tid == 0 ? m - 1 : (round + tid) % (m - 1);
-                int b = (round + m - 1 - tid) % (m - 1);
+                int a = round + tid, b = round + m - 1 - tid;           // both < 2 (m - 1): one conditional subtraction
+                if (a >= m - 1) a -= m - 1;
+                if (b >= m - 1) b -= m - 1;
+                if (tid == 0) a = m - 1;
                 if (a > b) { const int t = a; a = b; b = t; }
                 double c = 1.0, s = 0.0;
                 if (b < q) {
                     const float apq = (float)A[a][b], diff = (float)(A[b][b] - A[a][a]);
                     if (apq != 0.f) {
-                        const float tau = diff / (2.f * apq);
-                        const float tf = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-                        if (tf == tf) {                                  // inf / inf cannot occur; guard anyway
+                        const float tau = __fdividef(diff, 2.f * apq);
+                        const float tf = __fdividef(copysignf(1.f, tau), fabsf(tau) + __fsqrt_rn(fmaf(tau, tau, 1.f)));
+                        if (tf == tf) {                                  // (0 / 0 cannot occur; guard anyway)
                             const double t = (double)tf;
-                            c = rsqrt(1.0 + t * t);
+                            c = fast_rsqrt(fma(t, t, 1.0));
                             s = t * c;
                         }
                     }
