@@ -359,8 +359,13 @@ colsum_spec_chain_kernel(const float *__restrict__ a0, const float *__restrict__
                     const int first = (p == 0 && b == 0) ? 1 : 0;              // row 0 started the accumulator
                     const int cnt = (int)max((int64_t)0, min((int64_t)32, r_hi - r0));
                     if (cnt == 32 && first == 0) {
+                        // all 32 broadcasts first (independent), then the dependent adds: the shuffles of the next block
+                        // overlap the add chain of this one
+                        float v[32];
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur[b], q));
+                        for (int q = 0; q < 32; ++q) v[q] = __shfl_sync(0xffffffffu, cur[b], q);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc = __fadd_rn(acc, v[q]);
                     } else {
                         for (int q = first; q < cnt; ++q) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, cur[b], q));
                     }
