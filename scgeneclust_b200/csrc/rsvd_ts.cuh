@@ -299,7 +299,17 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 const uint32_t raw_tile = smem_base + rs * TS_RAW_BYTES;
                 const uint32_t raw_row = raw_tile + row_off;
                 const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
-                mbar_wait_park(bar_raw_full + 8 * rs, (uint32_t)(gs / TS_RAW_STAGES) & 1);
+                // The slot's previous use (stage gs - TS_RAW_STAGES) was consumed by ANOTHER group, so this group has never
+                // waited for that load: a parity wait alone would pass at once if that earlier load were still in flight
+                // (the barrier one phase behind - TMA loads complete out of order, and under memory-system contention,
+                // e.g. NVLink traffic of a collective, a load was seen to land later than the one issued three stages
+                // after it: one stage of stale counts, a 1e-5 wobble of the pass and, at 8 GPUs, a rank-deficient
+                // panel).  Waiting for the previous phase first pins the barrier to the right lap; it cannot be two laps
+                // behind, because the load of stage gs - 4, which this group did wait for, was issued after stage
+                // gs - 7, whose issue needed the slot's use before that to be consumed.
+                const uint32_t raw_par = (uint32_t)(gs / TS_RAW_STAGES) & 1;
+                mbar_wait_park(bar_raw_full + 8 * rs, raw_par ^ 1);
+                mbar_wait_park(bar_raw_full + 8 * rs, raw_par);
 #pragma unroll
                 for (int c2 = 0; c2 < TC_TK / 16; ++c2) {             // 16 entries (k = 16 c2 .. 16 c2 + 15) per round
                     uint32_t hi[8], lo[8];
