@@ -51,7 +51,15 @@ constexpr int TS_PRODUCER_WARPS = 4 * TS_GROUPS;
 constexpr int TS_EPI_WARPS = TS_EPI_WARPS_N;                     // one per TMEM lane quarter
 constexpr int TS_MMA_WARP = TS_PRODUCER_WARPS + TS_EPI_WARPS;
 constexpr int TS_THREADS = (TS_PRODUCER_WARPS + TS_EPI_WARPS + 3) * 32;
-constexpr int TS_RAW_STAGES = 7;                                 // raw count tiles in flight (TMA runs this far ahead)
+// Raw count tiles in flight (the TMA runs this far ahead).  MUST be a multiple of the number of producer groups: stage gs
+// goes to group gs % TS_GROUPS and to slot gs % TS_RAW_STAGES, and a parity wait on the slot's full barrier is only safe
+// for a waiter that has itself waited for the slot's PREVIOUS load.  With 7 (or 9) slots and 4 groups the previous use
+// of a slot belonged to another group: when that earlier load was still in flight - TMA loads complete out of order, and
+// under memory-system contention (NVLink traffic of a collective next door) one was seen to land later than the load
+// issued three stages after it - the barrier was one phase behind, the parity test passed at once and the group consumed
+// a stale tile: a 1e-5 wobble of one pass, run-to-run differences of the gene-sharded PCA and, at 8 GPUs with a million
+// cells, a rank-deficient panel.  (Single-GPU runs never showed it: 41 of 41 repetitions bit-identical.)
+constexpr int TS_RAW_STAGES = 8;
 constexpr int TS_B_STAGES = 4;
 constexpr int TS_RAW_BYTES = TC_TM * TC_TK * 2;                  // 16 KB raw uint16 tile
 constexpr int TS_PANEL_BYTES = 2 * TC_B_BYTES;                   // 16 KB [Q_hi | Q_lo]
@@ -62,7 +70,11 @@ constexpr int TS_OFF_ACC = TS_OFF_KC + TS_RAW_STAGES * TS_KC_BYTES;         // e
 constexpr int TS_ACC_BYTES = TS_EPI_WARPS_N * TC_TN * 32 * 4;
 constexpr int TS_OFF_BAR = TS_OFF_ACC + TS_ACC_BYTES;
 constexpr int TS_N_BARS = 2 * TS_RAW_STAGES + 2 * TS_A_STAGES + 2 * TS_B_STAGES + 2;
-constexpr int TS_SMEM_BYTES = TS_OFF_BAR + 8 * TS_N_BARS + 16 + 1024 /*align*/;
+// the tiles want a 1024-byte aligned base (SWIZZLE_128B).  The dynamic shared-memory window of a kernel without static
+// shared memory starts 1024-byte aligned; the slack covers an offset of up to 512 bytes and the kernel traps beyond it
+constexpr int TS_SMEM_USED = TS_OFF_BAR + 8 * TS_N_BARS + 16;
+constexpr int TS_SMEM_BYTES = TS_SMEM_USED + 512;
+static_assert(TS_RAW_STAGES % TS_GROUPS == 0, "every raw slot must belong to one producer group (see TS_RAW_STAGES)");
 constexpr int TS_ACC_COLS = 192, TS_A_COLS = 64;   // D1 = [0, 128): A_hi [Q_hi | Q_lo];  D2 = [128, 192): A_lo Q_hi
 static_assert(TS_ACC_COLS + TS_A_STAGES * TS_A_COLS <= TC_TMEM_COLS, "TMEM budget");
 static_assert(TS_THREADS <= 1024, "too many warps");
@@ -222,6 +234,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    if (smem_base - smem_u32(smem_raw) > (uint32_t)(TS_SMEM_BYTES - TS_SMEM_USED)) __trap();     // see TS_SMEM_BYTES
     const uint32_t bar_base = smem_base + TS_OFF_BAR;
     const uint32_t bar_raw_full = bar_base, bar_raw_empty = bar_raw_full + 8 * TS_RAW_STAGES;
     const uint32_t bar_a_full = bar_raw_empty + 8 * TS_RAW_STAGES, bar_a_empty = bar_a_full + 8 * TS_A_STAGES;
@@ -299,17 +312,9 @@ rsvd_apply_ts_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a) {
                 const uint32_t raw_tile = smem_base + rs * TS_RAW_BYTES;
                 const uint32_t raw_row = raw_tile + row_off;
                 const uint32_t kc_s = smem_base + TS_OFF_KC + rs * TS_KC_BYTES;
-                // The slot's previous use (stage gs - TS_RAW_STAGES) was consumed by ANOTHER group, so this group has never
-                // waited for that load: a parity wait alone would pass at once if that earlier load were still in flight
-                // (the barrier one phase behind - TMA loads complete out of order, and under memory-system contention,
-                // e.g. NVLink traffic of a collective, a load was seen to land later than the one issued three stages
-                // after it: one stage of stale counts, a 1e-5 wobble of the pass and, at 8 GPUs, a rank-deficient
-                // panel).  Waiting for the previous phase first pins the barrier to the right lap; it cannot be two laps
-                // behind, because the load of stage gs - 4, which this group did wait for, was issued after stage
-                // gs - 7, whose issue needed the slot's use before that to be consumed.
-                const uint32_t raw_par = (uint32_t)(gs / TS_RAW_STAGES) & 1;
-                mbar_wait_park(bar_raw_full + 8 * rs, raw_par ^ 1);
-                mbar_wait_park(bar_raw_full + 8 * rs, raw_par);
+                // (the slot belongs to this group alone - see TS_RAW_STAGES - so the group has itself waited for the slot's
+                // previous load and the parity cannot be read one lap off)
+                mbar_wait_park(bar_raw_full + 8 * rs, (uint32_t)(gs / TS_RAW_STAGES) & 1);
 #pragma unroll
                 for (int c2 = 0; c2 < TC_TK / 16; ++c2) {             // 16 entries (k = 16 c2 .. 16 c2 + 15) per round
                     uint32_t hi[8], lo[8];
