@@ -59,19 +59,16 @@ chol_inv_kernel(const double *__restrict__ Gm, int q, float *__restrict__ Rinv, 
         const double rs = rdiag[j];
         if (i > j && i < q) {
             const double w = -(A[i][j] * (rs * rs));
-            // the owner of the next pivot updates it first and forms its reciprocal square root - the one long
-            // dependent chain of the step - before its other entries
-            const bool owns_pivot = i == j + 1 && l == (i & 15);
-            if (owns_pivot) {
-                const double v = fma(w, A[i][j], A[i][i]);
-                A[i][i] = v;
-                pivot_rsqrt(v, i);
-            }
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const int c = l + 16 * m;
-                if (c <= j) X[i][c] = fma(w, X[j][c], X[i][c]);
-                else if (c <= i && !(owns_pivot && c == i)) A[i][c] = fma(w, A[c][j], A[i][c]);
+                if (c <= j) {
+                    X[i][c] = fma(w, X[j][c], X[i][c]);
+                } else if (c <= i) {
+                    const double v = fma(w, A[c][j], A[i][c]);
+                    A[i][c] = v;
+                    if (i == j + 1 && c == i) pivot_rsqrt(v, i);     // the next pivot: its owner forms 1 / sqrt right away
+                }
             }
         }
         __syncthreads();
