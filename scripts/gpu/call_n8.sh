@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU call: per-stage table + kernel list at N=8, bench N=8 (parity block), config c5 + subsample check, NCCL dist tests
 cd "$GRAFT_REPO_ROOT" || exit 1
-O=gpurun_out/r2n8b
+O=gpurun_out/r2n8c
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port"
