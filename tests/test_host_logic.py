@@ -289,3 +289,50 @@ def test_speculative_cumsum_prototype_is_bit_exact():
         carry = 0.0 if trial % 3 else float(np.float32(rs.gamma(2.0, 1e5)))
         reals.append(mod.check(v, carry))          # asserts bit equality at every piece boundary
     assert np.mean(reals) < 20                     # and most pieces are resolved without a real chain
+
+
+def test_mt19937_jump_polynomial_header_is_current():
+    """csrc/mt_jump_poly.h (the GF(2) jump polynomial that lets the Omega stream run in parallel segments) must be what
+    scripts/mt_jump_poly.py derives - Berlekamp-Massey on the generator's own output, square-and-multiply, and a check of
+    the jump identity against a directly generated sequence."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("mt_jump_poly", os.path.join(root, "scripts", "mt_jump_poly.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    header = open(os.path.join(root, "scgeneclust_b200", "csrc", "mt_jump_poly.h")).read()
+    words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]{8})u", header)]
+    assert len(words) == 624 and f"kMtSegBlocks = {mod.SEG_BLOCKS}" in header
+    g = sum(w << (32 * i) for i, w in enumerate(words))
+    taps = np.array([i for i in range(mod.DEG) if (g >> i) & 1], dtype=np.int64)
+    seq = mod.sequence(99, mod.SEG_BLOCKS + 40)
+    for k in (0, 1000):
+        for w in (0, 17, 623):
+            assert np.bitwise_xor.reduce(seq[k + taps + w]) == seq[k + mod.J + w]
+    # and the generator the script uses is numpy's: tempered words of the first block
+    rs = np.random.RandomState(99)
+    y = seq[:4].astype(np.uint64)
+    y ^= y >> np.uint64(11)
+    y ^= (y << np.uint64(7)) & np.uint64(0x9d2c5680)
+    y ^= (y << np.uint64(15)) & np.uint64(0xefc60000)
+    y ^= y >> np.uint64(18)
+    assert np.array_equal(y.astype(np.uint32), rs.randint(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32))
+
+
+def test_piece_parallel_float32_sum_prototype_is_exact():
+    """scripts/proto/spec_colsum.py: the integer-delta summary of a piece under a guessed binade, verified piece by piece,
+    returns the bits of the sequential float32 sum on ties, sign changes and binade crossings (the device version is
+    csrc/deviance_kernels.cu colsum_spec_*; its GPU test is tests/test_gpu_e2e.py::test_sum_axis0_is_numpy_sequential_sum)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("spec_colsum", os.path.join(root, "scripts", "proto", "spec_colsum.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rs = np.random.RandomState(3)
+    cases = [rs.standard_normal(700).astype(np.float32),
+             (np.abs(rs.standard_normal(900)) * 3).astype(np.float32),
+             np.concatenate([[np.float32(2 ** 20)], (rs.randint(-3, 4, 800) * 2.0 ** -4).astype(np.float32)]),
+             np.concatenate([[np.float32(1.0)], (rs.randint(-1, 2, 600) * 2.0 ** -24).astype(np.float32)])]
+    for x in cases:
+        assert mod.seq_sum(x).view(np.uint32) == mod.spec_sum(x).view(np.uint32)
