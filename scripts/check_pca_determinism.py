@@ -3,9 +3,9 @@ normalisation is checksummed on the device (no extra synchronisation), the check
 at the end and the first call that differs is named.  Stand-alone (one GPU) or under torchrun; `--same-device` = all ranks
 on cuda:0 with gloo.
 
-    python scripts/debug_sharded_pca.py 1000000 3776 10
+    python scripts/check_pca_determinism.py 1000000 3776 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
-        scripts/debug_sharded_pca.py 1000000 7552 8"""
+        scripts/check_pca_determinism.py 1000000 7552 8"""
 import os
 import sys
 

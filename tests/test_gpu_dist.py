@@ -71,14 +71,14 @@ def test_two_ranks_geneclust_ps_sharded_equals_single():
 
 def test_pca_is_run_to_run_deterministic():
     """Every raw pass and panel normalisation of the PCA must return the same bits in every repetition
-    (scripts/debug_sharded_pca.py checksums them on the device).  Regression test of a stale-tile hazard in the pass
+    (scripts/check_pca_determinism.py checksums them on the device).  Regression test of a stale-tile hazard in the pass
     kernel's raw-tile ring that only showed under memory-system contention (2 of 15 gene-sharded runs over NCCL)."""
     torch = _need_cuda()
-    script = os.path.join(ROOT, "scripts", "debug_sharded_pca.py")
+    script = os.path.join(ROOT, "scripts", "check_pca_determinism.py")
     res = subprocess.run([sys.executable, script, "300000", "3776", "6"], cwd=ROOT, stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True, timeout=600)
     print(res.stdout[-1500:])
     assert res.returncode == 0 and "DIFFERS" not in res.stdout and res.stdout.count("identical (") == 5
     if torch.cuda.device_count() >= 2:
-        res = _torchrun(["600000", "7552", "8"], script="debug_sharded_pca.py")
+        res = _torchrun(["600000", "7552", "8"], script="check_pca_determinism.py")
         assert res.returncode == 0 and "DIFFERS" not in res.stdout and res.stdout.count("identical (") == 7, res.stdout[-2000:]
