@@ -18,6 +18,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 C, G, K = 20_000, 20_000, 200
+_shape = [a for a in sys.argv[1:] if a.isdigit()]
+if len(_shape) >= 2:                                   # python scripts/cpu_noise_floor.py 20000 30000
+    C, G = int(_shape[0]), int(_shape[1])
 
 if len(sys.argv) > 1 and sys.argv[1] == "--worker":
     from oracle import stages
@@ -25,7 +28,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "--worker":
     X = osy.synth_counts_c(osy.synth_params(G, 0), 0, C, 0, G)
     names = np.array([f"g{i}" for i in range(G)], dtype=object)
     r = stages.geneclust_fast(X, names, K, 0)
-    np.savez(sys.argv[2], X_pca=r['X_pca'], labels=r['labels'], selected=r['selected'].astype(str))
+    # and the clustering of the OTHER run's embedding with this run's BLAS thread count (argv[5], optional): is the tail
+    # alone thread-count independent?
+    extra = {}
+    if len(sys.argv) > 5 and os.path.exists(sys.argv[5]):
+        E_other = np.load(sys.argv[5])['X_pca']
+        extra['labels_on_other'] = stages.kmeans_genes(E_other, K, 0)[0]
+    np.savez(sys.argv[2], X_pca=r['X_pca'], labels=r['labels'], selected=r['selected'].astype(str), **extra)
     sys.exit(0)
 
 from sklearn.metrics import adjusted_rand_score  # noqa: E402
@@ -36,12 +45,16 @@ out = {}
 for threads in ("8", "3"):
     path = f"/tmp/cpu_noise_{threads}.npz"
     env = dict(os.environ, OMP_NUM_THREADS=threads, OPENBLAS_NUM_THREADS=threads)
-    subprocess.run([sys.executable, __file__, "--worker", path], check=True, env=env)
+    subprocess.run([sys.executable, __file__, "--worker", path, str(C), str(G), "/tmp/cpu_noise_8.npz"], check=True, env=env)
     out[threads] = np.load(path)
 a, b = out["8"], out["3"]
 rel = np.linalg.norm(a['X_pca'] - b['X_pca'], axis=0) / np.linalg.norm(b['X_pca'], axis=0)
 print(f"CPU 8 vs 3 threads: PCA rel err max {rel.max():.2e}, first 10 PCs {rel[:10].max():.2e}, labels equal "
       f"{np.array_equal(a['labels'], b['labels'])}, ARI {adjusted_rand_score(a['labels'], b['labels']):.3f}")
+print(f"selected lists equal {np.array_equal(a['selected'], b['selected'])} ({len(a['selected'])} / {len(b['selected'])} genes)")
+if 'labels_on_other' in b.files:
+    print(f"k-means with 3 BLAS threads on the 8-thread run's embedding: labels identical to the 8-thread run's "
+          f"{np.array_equal(b['labels_on_other'], a['labels'])}, ARI {adjusted_rand_score(b['labels_on_other'], a['labels']):.4f}")
 E, lab0 = a['X_pca'], a['labels']
 rs = np.random.RandomState(1)
 for eps in (1e-7, 1e-6, 1e-5, 1e-4):
